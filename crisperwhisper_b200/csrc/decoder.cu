@@ -1,0 +1,786 @@
+// decoder.cu — stage 2b: greedy decode with the alignment-head cross-attention rows retained.
+//
+// Replaces, per generated token: WhisperDecoder.forward / WhisperDecoderLayer.forward / proj_out
+// (HF/models/whisper/modeling_whisper.py:691-796, :449-506, :1081), GenerationMixin._sample's loop body
+// (HF/generation/utils.py:2743-2800) and the three Whisper logits processors
+// (HF/generation/logits_process.py:1847-1862, 1894-1902, 1963-2043).
+//
+// The step is HBM-bound (decoder weights once per step + the cross-attention K/V of every sample); its kernels:
+//   embed_kernel        x = tok_emb[token] + pos[p]                                               (:738-763)
+//   gemv_kernel<NT,EPI> weight-streaming skinny GEMM for B <= 8*NT samples on mma.sync.m16n8k16: each weight
+//                       element is read exactly once straight from HBM into the A fragment (no smem staging), the
+//                       (optionally LayerNorm-ed) activations are the B operand from shared memory, K is split
+//                       across the warps of a CTA and reduced through shared memory. Epilogues: q/k/v split with
+//                       KV-cache append, fp32 store, residual add, GELU->bf16, logits.
+//   self_attn_kernel    causal attention over the bf16 self KV cache
+//   cross_attn_kernel   attention over the 1500 encoder frames; the softmax probabilities of the alignment heads
+//                       are written straight into align_out[b, slot, s, :] (fp32) — HF instead retains all
+//                       32x20 heads of every step (utils.py:2778) and gathers afterwards (generation_whisper.py:254-261)
+//   sample_kernel       suppress lists + timestamp rules + fp32 log-softmax rule + argmax + EOS bookkeeping
+// One decode step is captured once into a CUDA graph; the position lives in device memory, so the same graph is
+// replayed for every step (cudaGraphLaunch), with the host polling the "all finished" counter every 16 steps.
+#include "common.cuh"
+
+namespace cw {
+
+static constexpr int kGemvThreadsMax = 256;
+enum { EPI_QKV = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GELU_BF16 = 3 };
+
+struct DecState {  // device-resident step state (ints)
+  int pos;         // position being processed (input token index)
+  int n_finished;
+  int pad[2];
+};
+
+struct GemvParams {
+  const bf16* W;        // [N, K]
+  const float* bias;    // [N] or null
+  int N, K, B;
+  // activation source: either f32 rows + LayerNorm, or bf16 rows
+  const float* x_f32;   // [B, K]
+  const float* ln_g;
+  const float* ln_b;
+  const bf16* x_bf16;   // [B, K]
+  // outputs
+  float* out_f32;       // EPI_F32 / EPI_RESID (x itself) / EPI_QKV (q)       [B, N or d]
+  bf16* out_bf16;       // EPI_GELU_BF16                                       [B, N]
+  bf16* kcache;         // EPI_QKV: [B, n_ctx, d] of this layer
+  bf16* vcache;
+  int d, n_ctx;
+  const DecState* st;
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float gelu_erf_d(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// smem: xs bf16 [8*NT][K + 32] | red f32 [warps][16][8*NT]
+template <int NT, int EPI>
+__global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int K = p.K;
+  const int XS = K + 32;  // row stride in elements: +64 B keeps the 16-byte B-fragment loads conflict-free
+  bf16* xs = reinterpret_cast<bf16*>(gsm);
+  float* red = reinterpret_cast<float*>(gsm + (size_t)8 * NT * XS * 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarps = blockDim.x >> 5;
+
+  // ---- phase 0: activations -> bf16 rows in smem (LayerNorm fused when requested) -------------------------
+  if (p.ln_g != nullptr) {
+    for (int b = warp; b < 8 * NT; b += nwarps) {
+      bf16* dst = xs + (size_t)b * XS;
+      if (b < p.B) {
+        const float* xr = p.x_f32 + (size_t)b * K;
+        float s = 0.f;
+        for (int k = lane; k < K; k += 32) s += xr[k];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)K;
+        float q = 0.f;
+        for (int k = lane; k < K; k += 32) { float dd = xr[k] - mean; q += dd * dd; }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / (float)K + 1e-5f);
+        for (int k = lane; k < K; k += 32)
+          dst[k] = __float2bfloat16((xr[k] - mean) * rstd * __ldg(p.ln_g + k) + __ldg(p.ln_b + k));
+      } else {
+        for (int k = lane; k < K; k += 32) dst[k] = __float2bfloat16(0.f);
+      }
+    }
+  } else {
+    const int vec_per_row = K >> 3;
+    for (int i = tid; i < 8 * NT * vec_per_row; i += blockDim.x) {
+      int b = i / vec_per_row, c = i - b * vec_per_row;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (b < p.B) v = *reinterpret_cast<const uint4*>(p.x_bf16 + (size_t)b * K + c * 8);
+      *reinterpret_cast<uint4*>(xs + (size_t)b * XS + c * 8) = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: 16 output rows per CTA, K split across warps ---------------------------------------------
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  const int kslice = K / nwarps;        // multiple of 32 (checked on the host)
+  const int kbeg = warp * kslice;
+  const int chunks = kslice >> 5;
+  const bf16* w0 = p.W + (size_t)(n0 + g) * K + kbeg + 8 * t;
+  const bf16* w1 = w0 + (size_t)8 * K;
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+  constexpr int U = 5;
+  for (int c0 = 0; c0 < chunks; c0 += U) {
+    uint4 a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u < chunks) {
+        a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+        a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u < chunks) {
+        const int kk = kbeg + (c0 + u) * 32 + 8 * t;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const uint4 xb = *reinterpret_cast<const uint4*>(xs + (size_t)(8 * j + g) * XS + kk);
+          // k-permutation: MMA slot pairs {2t,2t+1},{2t+8,2t+9} <-> actual k {8t+0,1},{8t+2,3} (then {8t+4..7})
+          mma16816(acc[j], a0[u].x, a1[u].x, a0[u].y, a1[u].y, xb.x, xb.y);
+          mma16816(acc[j], a0[u].z, a1[u].z, a0[u].w, a1[u].w, xb.z, xb.w);
+        }
+      }
+    }
+  }
+  // ---- cross-warp reduction + epilogue --------------------------------------------------------------------
+  constexpr int NB = 8 * NT;
+  float* myred = red + (size_t)warp * 16 * NB;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    myred[g * NB + 8 * j + 2 * t] = acc[j][0];
+    myred[g * NB + 8 * j + 2 * t + 1] = acc[j][1];
+    myred[(g + 8) * NB + 8 * j + 2 * t] = acc[j][2];
+    myred[(g + 8) * NB + 8 * j + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int o = tid; o < 16 * NB; o += blockDim.x) {
+    const int r = o & 15, bcol = o >> 4;
+    if (bcol >= p.B) continue;
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += red[(size_t)w * 16 * NB + r * NB + bcol];
+    const int n = n0 + r;
+    if (p.bias) v += __ldg(p.bias + n);
+    if (EPI == EPI_F32) {
+      p.out_f32[(size_t)bcol * p.N + n] = v;
+    } else if (EPI == EPI_RESID) {
+      p.out_f32[(size_t)bcol * p.N + n] += v;
+    } else if (EPI == EPI_GELU_BF16) {
+      p.out_bf16[(size_t)bcol * p.N + n] = __float2bfloat16(gelu_erf_d(v));
+    } else {  // EPI_QKV
+      const int d = p.d;
+      const int pos = p.st->pos;
+      if (n < d) p.out_f32[(size_t)bcol * d + n] = v;
+      else if (n < 2 * d) p.kcache[((size_t)bcol * p.n_ctx + pos) * d + (n - d)] = __float2bfloat16(v);
+      else p.vcache[((size_t)bcol * p.n_ctx + pos) * d + (n - 2 * d)] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const bf16* __restrict__ emb, const float* __restrict__ pos_tab, const int* __restrict__ seq,
+                             int seq_ld, const DecState* st, float* __restrict__ x, int d) {
+  const int b = blockIdx.x;
+  const int pos = st->pos;
+  const int tok = seq[(size_t)b * seq_ld + pos];
+  const bf16* e = emb + (size_t)tok * d;
+  const float* pp = pos_tab + (size_t)pos * d;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) x[(size_t)b * d + k] = __bfloat162float(e[k]) + pp[k];
+}
+
+// LayerNorm of B rows f32 -> bf16 (final decoder norm before proj_out, modeling_whisper.py:791)
+__global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
+                               bf16* __restrict__ out, int d) {
+  const int b = blockIdx.x;
+  const float* xr = x + (size_t)b * d;
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) s += xr[k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+  const float mean = tot / (float)d;
+  __syncthreads();
+  float q = 0.f;
+  for (int k = threadIdx.x; k < d; k += blockDim.x) { float dd = xr[k] - mean; q += dd * dd; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = q;
+  __syncthreads();
+  float qt = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) qt += sh[w];
+  const float rstd = rsqrtf(qt / (float)d + 1e-5f);
+  for (int k = threadIdx.x; k < d; k += blockDim.x)
+    out[(size_t)b * d + k] = __float2bfloat16((xr[k] - mean) * rstd * g[k] + bta[k]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// causal self-attention for one new token: grid (n_heads, B), 128 threads
+// q f32 [B, d] (pre-scaled), caches bf16 [B, n_ctx, d]; out bf16 [B, d]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) self_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kc,
+                                                       const bf16* __restrict__ vc, bf16* __restrict__ out,
+                                                       const DecState* st, int d, int n_ctx) {
+  __shared__ float sq[64];
+  __shared__ float sp[448];
+  __shared__ float sred[4];
+  __shared__ float so[2][64];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int n = st->pos + 1;  // keys 0..pos
+  if (tid < 64) sq[tid] = q[(size_t)b * d + h * 64 + tid];
+  __syncthreads();
+  const bf16* kb = kc + (size_t)b * n_ctx * d + h * 64;
+  const bf16* vb = vc + (size_t)b * n_ctx * d + h * 64;
+  float lmax = -INFINITY;
+  for (int j = tid; j < n; j += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * d);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u = kr[c];
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h2[e]);
+        s = fmaf(sq[c * 8 + 2 * e], f.x, s);
+        s = fmaf(sq[c * 8 + 2 * e + 1], f.y, s);
+      }
+    }
+    sp[j] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3]));
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = tid; j < n; j += 128) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((tid & 31) == 0) sred[tid >> 5] = lsum;
+  __syncthreads();
+  const float inv = 1.f / (sred[0] + sred[1] + sred[2] + sred[3]);
+  // out[dd] = sum_j p[j] v[j][dd]; two halves of the keys
+  const int dd = tid & 63, half = tid >> 6;
+  float acc = 0.f;
+  for (int j = half; j < n; j += 2) acc = fmaf(sp[j], __bfloat162float(vb[(size_t)j * d + dd]), acc);
+  so[half][dd] = acc;
+  __syncthreads();
+  if (tid < 64) out[(size_t)b * d + h * 64 + tid] = __float2bfloat16((so[0][tid] + so[1][tid]) * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cross-attention for one new token over F encoder frames: grid (n_heads, B), 256 threads
+// xkv layer slice: bf16 [B, F, 2, n_heads, 64];  q f32 [B, d] (pre-scaled);  out bf16 [B, d]
+// align_out f32 [B, H_a, T_cap, F]: row s = pos - n_prompt of slot align_map[h] gets the probabilities
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int kXThreads = 256;
+static constexpr int kFMax = 1500;
+
+__global__ void __launch_bounds__(kXThreads) cross_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ xkv,
+                                                              bf16* __restrict__ out, const DecState* st,
+                                                              const int* __restrict__ align_map_layer, float* align_out,
+                                                              int H_a, int T_cap, int n_prompt, int d, int F) {
+  __shared__ float sq[64];
+  __shared__ float sp[kFMax];
+  __shared__ float sred[8];
+  __shared__ float so[32][65];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int n_heads = d >> 6;
+  if (tid < 64) sq[tid] = q[(size_t)b * d + h * 64 + tid];
+  __syncthreads();
+  const size_t fstride = (size_t)2 * d;  // elements per frame (K | V)
+  const bf16* kb = xkv + (size_t)b * F * fstride + h * 64;
+  const bf16* vb = kb + d;
+  float lmax = -INFINITY;
+  for (int j = tid; j < F; j += kXThreads) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * fstride);
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = ldg_stream(kr + c);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[c]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __bfloat1622float2(h2[e]);
+        s = fmaf(sq[c * 8 + 2 * e], f.x, s);
+        s = fmaf(sq[c * 8 + 2 * e + 1], f.y, s);
+      }
+    }
+    sp[j] = s;
+    lmax = fmaxf(lmax, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((tid & 31) == 0) sred[tid >> 5] = lmax;
+  __syncthreads();
+  float mx = sred[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sred[w]);
+  __syncthreads();
+  float lsum = 0.f;
+  for (int j = tid; j < F; j += kXThreads) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((tid & 31) == 0) sred[tid >> 5] = lsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += sred[w];
+  const float inv = 1.f / tot;
+  // normalised probabilities (needed both for the output and for the alignment rows)
+  for (int j = tid; j < F; j += kXThreads) sp[j] *= inv;
+  __syncthreads();
+  const int slot = align_map_layer[h];
+  const int s_row = st->pos - n_prompt;
+  if (slot >= 0 && s_row >= 0 && s_row < T_cap && align_out != nullptr) {
+    float* dst = align_out + (((size_t)b * H_a + slot) * T_cap + s_row) * F;
+    for (int j = tid; j < F; j += kXThreads) dst[j] = sp[j];
+  }
+  // out[dd] = sum_j p[j] V[j][dd]: 8 threads per frame row (16 B each), 32 frame rows in flight
+  const int sub = tid & 7, grp = tid >> 3;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j = grp; j < F; j += 32) {
+    uint4 u = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * fstride) + sub);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float pj = sp[j];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __bfloat1622float2(h2[e]);
+      acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) so[grp][sub * 8 + e] = acc[e];
+  __syncthreads();
+  if (tid < 64) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) v += so[r][tid];
+    out[(size_t)b * d + h * 64 + tid] = __float2bfloat16(v);
+  }
+  (void)n_heads;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sampling: logits processors + argmax + bookkeeping. One CTA (1024 threads) per sample.
+// ---------------------------------------------------------------------------------------------------------
+struct SampleParams {
+  float* logits;            // [B, Vp] in/out (processed in place)
+  const uint8_t* suppress;  // [Vp] bit0 always, bit1 at begin, bit2 padding row
+  int* seq; int seq_ld;     // [B, seq_ld]
+  int* finished;            // [B]
+  DecState* st;
+  int V, Vp, n_prompt, max_new, eos, no_ts, max_initial_ts, flags;
+  const int* forced;        // [B, max_new] or null
+  float* logits_out;        // [B, max_new, V] or null
+  int* argmax_out;          // [B, max_new] or null
+};
+
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+  return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
+  __shared__ float sh[32];
+  __shared__ int sh_i[32];
+  __shared__ float sh_v[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int pos = p.st->pos;
+  const int step = pos - (p.n_prompt - 1);   // index of the token this step generates
+  if (step < 0 || step >= p.max_new) return; // prompt prefill: nothing to sample
+  float* lg = p.logits + (size_t)b * p.Vp;
+  int* seq = p.seq + (size_t)b * p.seq_ld;
+  const int cur_len = pos + 1;               // tokens in the sequence so far
+  const int ts_begin = p.no_ts + 1;
+  const float NEG = -INFINITY;
+  const bool at_begin = (cur_len == p.n_prompt);
+  const bool ts_rules = !(p.flags & CW_DEC_NO_TIMESTAMP_RULES);
+
+  // history of sampled tokens (logits_process.py:2003-2010)
+  const int n_sampled = cur_len - p.n_prompt;
+  const int last = n_sampled >= 1 ? seq[cur_len - 1] : -1;
+  const int penult = n_sampled >= 2 ? seq[cur_len - 2] : -1;
+  const bool last_was_ts = n_sampled >= 1 && last >= ts_begin;
+  const bool penult_was_ts = n_sampled < 2 || penult >= ts_begin;
+  // timestamps[-1]: the most recent sampled token >= ts_begin (:2015-2024)
+  int last_ts = -1;
+  if (ts_rules) {
+    int cand = -1;
+    for (int i = p.n_prompt + tid; i < cur_len; i += blockDim.x)
+      if (seq[i] >= ts_begin) cand = max(cand, i);
+    for (int o = 16; o > 0; o >>= 1) cand = max(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    __syncthreads();
+    if ((tid & 31) == 0) sh_i[tid >> 5] = cand;
+    __syncthreads();
+    int best = -1;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) best = max(best, sh_i[w]);
+    if (best >= 0) last_ts = seq[best];
+    __syncthreads();
+  }
+  int ts_last_excl = -1;  // scores[ts_begin : ts_last_excl] = -inf
+  if (last_ts >= 0) ts_last_excl = (last_was_ts && !penult_was_ts) ? last_ts : last_ts + 1;
+
+  // pass 1: masks
+  float lmax = NEG;
+  for (int i = tid; i < p.Vp; i += blockDim.x) {
+    float v = lg[i];
+    const uint8_t m = p.suppress[i];
+    bool kill = (m & 4) || (m & 1) || (at_begin && (m & 2));
+    if ((p.flags & CW_DEC_SUPPRESS_EOS) && i == p.eos) kill = true;
+    if (ts_rules) {
+      if (i == p.no_ts) kill = true;
+      if (last_was_ts) {
+        if (penult_was_ts) { if (i >= ts_begin) kill = true; }
+        else { if (i < p.eos) kill = true; }
+      }
+      if (ts_last_excl >= 0 && i >= ts_begin && i < ts_last_excl) kill = true;
+      if (at_begin) {
+        if (i < ts_begin) kill = true;
+        if (p.max_initial_ts >= 0 && i > ts_begin + p.max_initial_ts) kill = true;
+      }
+    }
+    if (kill) v = NEG;
+    lg[i] = v;
+    if (i < p.V) lmax = fmaxf(lmax, v);
+  }
+  __syncthreads();
+  if (ts_rules) {
+    // fp32 log_softmax, then logsumexp(timestamps) vs max(text) (:2036-2041)
+    const float M = block_reduce_max(lmax, sh);
+    float lsum = 0.f;
+    for (int i = tid; i < p.V; i += blockDim.x) lsum += expf(lg[i] - M);
+    const float Z = block_reduce_sum(lsum, sh);
+    const float lse = M + logf(Z);
+    float tmax = NEG, xmax = NEG;
+    for (int i = tid; i < p.V; i += blockDim.x) {
+      float lp = lg[i] - lse;
+      if (i >= ts_begin) tmax = fmaxf(tmax, lp); else xmax = fmaxf(xmax, lp);
+    }
+    const float TM = block_reduce_max(tmax, sh);
+    const float XM = block_reduce_max(xmax, sh);
+    float tsum = 0.f;
+    if (TM > NEG) {
+      for (int i = ts_begin + tid; i < p.V; i += blockDim.x) tsum += expf((lg[i] - lse) - TM);
+    }
+    const float TS = block_reduce_sum(tsum, sh);
+    const float ts_logprob = (TM > NEG) ? (logf(TS) + TM) : NEG;
+    if (ts_logprob > XM) {
+      for (int i = tid; i < ts_begin && i < p.V; i += blockDim.x) lg[i] = NEG;
+    }
+    __syncthreads();
+  }
+  // argmax (lowest index among maxima)
+  float bv = NEG; int bi = 0x7fffffff;
+  for (int i = tid; i < p.V; i += blockDim.x) {
+    float v = lg[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncthreads();
+  if ((tid & 31) == 0) { sh_v[tid >> 5] = bv; sh_i[tid >> 5] = bi; }
+  __syncthreads();
+  if (p.logits_out) {
+    float* dst = p.logits_out + ((size_t)b * p.max_new + step) * p.V;
+    for (int i = tid; i < p.V; i += blockDim.x) dst[i] = lg[i];
+  }
+  if (tid == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sh_v[w] > bv || (sh_v[w] == bv && sh_i[w] < bi)) { bv = sh_v[w]; bi = sh_i[w]; }
+    if (bi == 0x7fffffff) bi = p.eos;  // every score -inf/NaN: cannot happen with sane logits
+    if (p.argmax_out) p.argmax_out[(size_t)b * p.max_new + step] = bi;
+    int tok = p.forced ? p.forced[(size_t)b * p.max_new + step] : bi;
+    const int was_finished = p.finished[b];
+    if (was_finished) tok = p.eos;  // pad_token_id == eos for Whisper (utils.py:2795-2797)
+    seq[cur_len] = tok;
+    if (!was_finished && tok == p.eos) {
+      p.finished[b] = 1;
+      atomicAdd(&p.st->n_finished, 1);
+    }
+  }
+}
+
+__global__ void advance_kernel(DecState* st) { st->pos += 1; }
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct DecGraph {
+  cudaGraphExec_t exec;
+  // key
+  const void* xkv; const void* ws; int B, n_prompt, max_new, flags;
+  const void* forced; const void* align_out; const void* logits_out; const void* argmax_out; const void* tokens_out;
+  bool valid;
+};
+
+void decode_state_free(cw_ctx* ctx) {
+  if (ctx->dec_state) {
+    DecGraph* g = (DecGraph*)ctx->dec_state;
+    if (g->valid) cudaGraphExecDestroy(g->exec);
+    delete g;
+    ctx->dec_state = nullptr;
+  }
+}
+
+struct DecBuffers {
+  float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
+  bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
+};
+
+static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
+  Arena a(ws ? ws : (void*)nullptr, (size_t)-1);
+  char* base = (char*)ws;
+  auto take = [&](size_t bytes) -> void* { void* p = a.take(bytes); return base ? p : (void*)nullptr; };
+  const size_t d = m.d_model;
+  DecBuffers t;
+  t.x = (float*)take((size_t)B * d * 4);
+  t.qbuf = (float*)take((size_t)B * d * 4);
+  t.attn = (bf16*)take((size_t)B * d * 2);
+  t.hbuf = (bf16*)take((size_t)B * m.ffn_dim * 2);
+  t.xn = (bf16*)take((size_t)B * d * 2);
+  t.logits = (float*)take((size_t)B * m.vocab_padded * 4);
+  t.kc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);
+  t.vc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);
+  t.st = (DecState*)take(sizeof(DecState));
+  t.finished = (int*)take((size_t)B * 4);
+  t.seq = (int*)take((size_t)B * m.n_text_ctx * 4);
+  if (o) *o = t;
+  return a.off + 256;
+}
+
+size_t decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new) {
+  (void)max_new;
+  return dec_layout(ctx->md, B, nullptr, nullptr);
+}
+
+template <int NT>
+static int launch_gemv(cw_ctx* ctx, int epi, const GemvParams& p, cudaStream_t st) {
+  CW_REQUIRE(p.N % 16 == 0, CW_ERR_UNSUPPORTED, "gemv: N=%d must be a multiple of 16", p.N);
+  int nwarps = (p.K % 256 == 0) ? 8 : ((p.K % 128 == 0) ? 4 : 0);
+  CW_REQUIRE(nwarps > 0, CW_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 128", p.K);
+  size_t smem = (size_t)8 * NT * (p.K + 32) * 2 + (size_t)nwarps * 16 * 8 * NT * 4;
+  CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "gemv: smem %zu too large (K=%d)", smem, p.K);
+  dim3 grid(p.N / 16), block(nwarps * 32);
+#define CW_GEMV_LAUNCH(E)                                                                                         \
+  {                                                                                                               \
+    CW_CUDA(cudaFuncSetAttribute(gemv_kernel<NT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    gemv_kernel<NT, E><<<grid, block, smem, st>>>(p);                                                             \
+  }
+  switch (epi) {
+    case EPI_QKV: CW_GEMV_LAUNCH(EPI_QKV) break;
+    case EPI_F32: CW_GEMV_LAUNCH(EPI_F32) break;
+    case EPI_RESID: CW_GEMV_LAUNCH(EPI_RESID) break;
+    default: CW_GEMV_LAUNCH(EPI_GELU_BF16) break;
+  }
+#undef CW_GEMV_LAUNCH
+  CW_CHECK_LAUNCH("gemv_kernel");
+  ctx->launches += 1;
+  return CW_OK;
+}
+
+static int gemv(cw_ctx* ctx, int B, int epi, const GemvParams& p, cudaStream_t st) {
+  return (B <= 8) ? launch_gemv<1>(ctx, epi, p, st) : launch_gemv<2>(ctx, epi, p, st);
+}
+
+// enqueue the kernels of one decode step (position read from device memory)
+static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
+                        const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
+  const ModelDesc& m = ctx->md;
+  const int d = m.d_model, F = m.n_audio_ctx;
+  const void** W = ctx->w;
+  int rc;
+  embed_kernel<<<B, 256, 0, st>>>((const bf16*)W[CW_W_TOK_EMB], (const float*)W[CW_W_DEC_POS], bf.seq, m.n_text_ctx, bf.st,
+                                  bf.x, d);
+  CW_CHECK_LAUNCH("embed_kernel");
+  ctx->launches += 1;
+  const size_t cache_l = (size_t)B * m.n_text_ctx * d;
+  const size_t xkv_l = (size_t)B * F * 2 * d;
+  for (int l = 0; l < m.dec_layers; ++l) {
+    const void** L = W + CW_W_GLOBAL_COUNT + (size_t)m.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
+    GemvParams g;
+    // self-attention block
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_WQKV]; g.bias = (const float*)L[CW_DL_BQKV]; g.N = 3 * d; g.K = d; g.B = B;
+    g.x_f32 = bf.x; g.ln_g = (const float*)L[CW_DL_LN1_G]; g.ln_b = (const float*)L[CW_DL_LN1_B];
+    g.out_f32 = bf.qbuf; g.kcache = bf.kc + l * cache_l; g.vcache = bf.vc + l * cache_l; g.d = d; g.n_ctx = m.n_text_ctx;
+    g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_QKV, g, st)) != CW_OK) return rc;
+    self_attn_kernel<<<dim3(m.n_heads, B), 128, 0, st>>>(bf.qbuf, bf.kc + l * cache_l, bf.vc + l * cache_l, bf.attn, bf.st,
+                                                          d, m.n_text_ctx);
+    CW_CHECK_LAUNCH("self_attn_kernel");
+    ctx->launches += 1;
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_WO]; g.bias = (const float*)L[CW_DL_BO]; g.N = d; g.K = d; g.B = B;
+    g.x_bf16 = bf.attn; g.out_f32 = bf.x; g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_RESID, g, st)) != CW_OK) return rc;
+    // cross-attention block
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_WQC]; g.bias = (const float*)L[CW_DL_BQC]; g.N = d; g.K = d; g.B = B;
+    g.x_f32 = bf.x; g.ln_g = (const float*)L[CW_DL_LN2_G]; g.ln_b = (const float*)L[CW_DL_LN2_B];
+    g.out_f32 = bf.qbuf; g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_F32, g, st)) != CW_OK) return rc;
+    cross_attn_kernel<<<dim3(m.n_heads, B), kXThreads, 0, st>>>(bf.qbuf, xkv + l * xkv_l, bf.attn, bf.st,
+                                                                 ctx->d_align_map + (size_t)l * m.n_heads, align_out,
+                                                                 m.n_align_heads, max_new, n_prompt, d, F);
+    CW_CHECK_LAUNCH("cross_attn_kernel");
+    ctx->launches += 1;
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_WOC]; g.bias = (const float*)L[CW_DL_BOC]; g.N = d; g.K = d; g.B = B;
+    g.x_bf16 = bf.attn; g.out_f32 = bf.x; g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_RESID, g, st)) != CW_OK) return rc;
+    // feed-forward block
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_W1]; g.bias = (const float*)L[CW_DL_B1]; g.N = m.ffn_dim; g.K = d; g.B = B;
+    g.x_f32 = bf.x; g.ln_g = (const float*)L[CW_DL_LN3_G]; g.ln_b = (const float*)L[CW_DL_LN3_B];
+    g.out_bf16 = bf.hbuf; g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_GELU_BF16, g, st)) != CW_OK) return rc;
+    memset(&g, 0, sizeof(g));
+    g.W = (const bf16*)L[CW_DL_W2]; g.bias = (const float*)L[CW_DL_B2]; g.N = d; g.K = m.ffn_dim; g.B = B;
+    g.x_bf16 = bf.hbuf; g.out_f32 = bf.x; g.st = bf.st;
+    if ((rc = gemv(ctx, B, EPI_RESID, g, st)) != CW_OK) return rc;
+  }
+  ln_rows_kernel<<<B, 256, 0, st>>>(bf.x, (const float*)W[CW_W_DEC_LNF_G], (const float*)W[CW_W_DEC_LNF_B], bf.xn, d);
+  CW_CHECK_LAUNCH("ln_rows_kernel");
+  ctx->launches += 1;
+  GemvParams g;
+  memset(&g, 0, sizeof(g));
+  g.W = (const bf16*)W[CW_W_TOK_EMB]; g.bias = nullptr; g.N = m.vocab_padded; g.K = d; g.B = B;
+  g.x_bf16 = bf.xn; g.out_f32 = bf.logits; g.st = bf.st;
+  if ((rc = gemv(ctx, B, EPI_F32, g, st)) != CW_OK) return rc;
+  SampleParams sp;
+  sp.logits = bf.logits; sp.suppress = ctx->d_suppress; sp.seq = bf.seq; sp.seq_ld = m.n_text_ctx;
+  sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
+  sp.max_new = max_new; sp.eos = m.eos_id; sp.no_ts = m.no_timestamps_id; sp.max_initial_ts = m.max_initial_timestamp_index;
+  sp.flags = flags; sp.forced = forced; sp.logits_out = logits_out; sp.argmax_out = argmax_out;
+  sample_kernel<<<B, 1024, 0, st>>>(sp);
+  CW_CHECK_LAUNCH("sample_kernel");
+  advance_kernel<<<1, 1, 0, st>>>(bf.st);
+  CW_CHECK_LAUNCH("advance_kernel");
+  ctx->launches += 2;
+  return CW_OK;
+}
+
+__global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
+                                int eos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { st->pos = 0; st->n_finished = 0; }
+  if (i < B) finished[i] = 0;
+  if (i < B * seq_ld) {
+    int b = i / seq_ld, t = i - b * seq_ld;
+    seq[i] = (t < n_prompt) ? prompt[b * n_prompt + t] : eos;
+  }
+}
+
+__global__ void dec_finish_kernel(const int* seq, int seq_ld, int n_prompt, int total, int eos, int* tokens_out, int* len_out,
+                                  int B, int steps_done) {
+  // tokens_out [B, total]; len = prompt + generated tokens up to and including the first eos (or all generated)
+  int b = blockIdx.x;
+  if (b >= B) return;
+  const int n_gen = steps_done;  // tokens generated for every row
+  for (int t = threadIdx.x; t < total; t += blockDim.x)
+    tokens_out[(size_t)b * total + t] = (t < n_prompt + n_gen) ? seq[(size_t)b * seq_ld + t] : eos;
+  if (threadIdx.x == 0) {
+    int len = n_prompt + n_gen;
+    for (int t = n_prompt; t < n_prompt + n_gen; ++t)
+      if (seq[(size_t)b * seq_ld + t] == eos) { len = t + 1; break; }
+    len_out[b] = len;
+  }
+}
+
+int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n_prompt, int max_new, int flags,
+               const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out, float* logits_out,
+               int32_t* argmax_out, int* steps_out_host, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const ModelDesc& m = ctx->md;
+  CW_REQUIRE(xkv && prompt && tokens_out && len_out, CW_ERR_INVALID, "cw_decode_greedy: NULL argument");
+  CW_REQUIRE(B >= 1 && B <= 16, CW_ERR_UNSUPPORTED, "cw_decode_greedy: B=%d outside [1,16] (split the batch)", B);
+  CW_REQUIRE(n_prompt >= 1 && max_new >= 1 && n_prompt + max_new <= m.n_text_ctx, CW_ERR_INVALID,
+             "cw_decode_greedy: n_prompt=%d max_new=%d exceed n_text_ctx=%d", n_prompt, max_new, m.n_text_ctx);
+  size_t need = decode_workspace_bytes(ctx, B, max_new);
+  CW_REQUIRE(ws && ws_bytes >= need, CW_ERR_WORKSPACE, "cw_decode_greedy: workspace %zu < %zu", ws_bytes, need);
+  DecBuffers bf;
+  dec_layout(m, B, &bf, ws);
+
+  int n_init = B * m.n_text_ctx;
+  dec_init_kernel<<<(n_init + 255) / 256, 256, 0, st>>>(bf.st, bf.finished, bf.seq, m.n_text_ctx, prompt, n_prompt, B,
+                                                        m.eos_id);
+  CW_CHECK_LAUNCH("dec_init_kernel");
+  ctx->launches += 1;
+
+  const int total_steps = n_prompt - 1 + max_new;  // positions 0 .. n_prompt+max_new-2
+  // stream capture is not available on the legacy / per-thread default streams
+  const bool use_graph = !(flags & CW_DEC_NO_GRAPH) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  int rc = CW_OK;
+  DecGraph* G = (DecGraph*)ctx->dec_state;
+  if (use_graph) {
+    bool hit = G && G->valid && G->xkv == xkv && G->ws == ws && G->B == B && G->n_prompt == n_prompt &&
+               G->max_new == max_new && G->flags == flags && G->forced == forced && G->align_out == align_out &&
+               G->logits_out == logits_out && G->argmax_out == argmax_out;
+    if (!hit) {
+      if (!G) { G = new DecGraph(); G->valid = false; ctx->dec_state = G; }
+      if (G->valid) { cudaGraphExecDestroy(G->exec); G->valid = false; }
+      // every kernel attribute must be set before capture: run one un-captured "dry" configuration pass is not
+      // needed because cudaFuncSetAttribute is legal during capture (it is not a stream operation).
+      cudaGraph_t graph;
+      long long launches_before = ctx->launches;
+      CW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      ctx->launches = launches_before;  // capture does not execute anything
+      if (rc != CW_OK) { if (ce == cudaSuccess && graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+      ce = cudaGraphInstantiate(&G->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+      G->valid = true;
+      G->xkv = xkv; G->ws = ws; G->B = B; G->n_prompt = n_prompt; G->max_new = max_new; G->flags = flags;
+      G->forced = forced; G->align_out = align_out; G->logits_out = logits_out; G->argmax_out = argmax_out;
+    }
+  }
+  const long long per_step = 5 + 8LL * m.dec_layers;  // kernels in one step
+  int steps_done = 0;  // generated tokens
+  int h_state[4] = {0, 0, 0, 0};
+  for (int s = 0; s < total_steps; ++s) {
+    if (use_graph) {
+      CW_CUDA(cudaGraphLaunch(G->exec, st));
+      ctx->launches += per_step;
+    } else {
+      rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+      if (rc != CW_OK) return rc;
+    }
+    if (s >= n_prompt - 1) steps_done = s - (n_prompt - 1) + 1;
+    const bool poll = !(flags & CW_DEC_SUPPRESS_EOS) && forced == nullptr && ((s & 15) == 15);
+    if (poll) {
+      CW_CUDA(cudaMemcpyAsync(h_state, bf.st, sizeof(DecState), cudaMemcpyDeviceToHost, st));
+      CW_CUDA(cudaStreamSynchronize(st));
+      if (h_state[1] >= B) break;
+    }
+  }
+  dec_finish_kernel<<<B, 128, 0, st>>>(bf.seq, m.n_text_ctx, n_prompt, n_prompt + max_new, m.eos_id, tokens_out, len_out, B,
+                                       steps_done);
+  CW_CHECK_LAUNCH("dec_finish_kernel");
+  ctx->launches += 1;
+  CW_CUDA(cudaStreamSynchronize(st));
+  if (steps_out_host) *steps_out_host = steps_done;
+  return CW_OK;
+}
+
+}  // namespace cw
