@@ -1,0 +1,195 @@
+"""Generate tests/golden/*.npz|json by running the REFERENCE itself in this container:
+  * the installed transformers 5.5.0 functions the reference's pipeline executes (the arithmetic of the hot path), and
+  * /root/reference/utils.py (adjust_pauses_for_hf_pipeline_output) imported from the read-only reference checkout.
+The reference ships no golden vectors of its own, so these files are the pin.  Re-run with
+    python tests/golden/make_golden.py
+Nothing here is needed at test time on the GPU box: the tests only read the committed files.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+sys.path.insert(0, ROOT)
+
+from oracle import hf_harness as H  # noqa: E402
+
+
+def align_case(seed, H_, T, F, peak=6.0, noise=3.0, zero_cols=0):
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((H_, T, F))
+    t = np.arange(T)[None, :, None]
+    f = np.arange(F)[None, None, :]
+    logit = noise * z + peak * np.exp(-(((f - t * F / max(T, 1)) / 20.0) ** 2))
+    w = torch.softmax(torch.from_numpy(logit.astype(np.float32)), -1).numpy()
+    if zero_cols:
+        w[:, :, -zero_cols:] = 0.0  # all-zero columns -> std 0 -> NaN columns in the reference
+    return w
+
+
+def gen_align():
+    from transformers import WhisperForConditionalGeneration
+    from transformers.generation.utils import GenerateEncoderDecoderOutput
+    m = WhisperForConditionalGeneration(H.tiny_hf_config(d_model=128, heads=4, layers=2)).eval()
+    cases = [
+        # (name, seed, H, T, F_full, num_frames(list per N), median_w, zero_cols, n_prompt)
+        ("basic", 1, 4, 24, 200, [400], 7, 0, 3),
+        ("w3", 2, 3, 17, 160, [320], 3, 0, 3),
+        ("crop", 3, 4, 20, 220, [440, 300, 181], 7, 0, 3),
+        ("t1", 4, 4, 1, 120, [240], 7, 0, 3),
+        ("t2", 5, 4, 2, 120, [240], 7, 0, 1),
+        ("tinyF", 6, 2, 5, 3, [6], 7, 0, 3),
+        ("F4", 7, 2, 5, 4, [8], 7, 0, 3),
+        ("nancols", 8, 4, 12, 150, [300], 7, 20, 3),
+        ("t33", 9, 8, 33, 300, [600], 7, 0, 3),
+        ("w1", 10, 2, 9, 64, [128], 1, 0, 3),
+    ]
+    out = {}
+    for name, seed, Hh, T, F, nfs, mw, zc, n_prompt in cases:
+        N = len(nfs)
+        w = np.stack([align_case(seed * 100 + n, Hh, T, F, zero_cols=zc) for n in range(N)])
+        m.config.median_filter_width = mw
+        layers = [torch.zeros(N, 4, n_prompt + T, F) for _ in range(2)]
+        heads = []
+        for i in range(Hh):
+            layers[i // 4][:, i % 4, n_prompt:] = torch.from_numpy(w[:, i])
+            heads.append([i // 4, i % 4])
+        go = GenerateEncoderDecoderOutput(sequences=torch.zeros(N, n_prompt + T + 1, dtype=torch.long),
+                                          cross_attentions=(tuple(layers),))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ts = m._extract_token_timestamps(go, heads, num_frames=torch.tensor(nfs), num_input_ids=n_prompt).numpy()
+        out[f"{name}.w"] = w
+        out[f"{name}.num_frames"] = np.array(nfs, np.int32)
+        out[f"{name}.median"] = np.array(mw, np.int32)
+        out[f"{name}.n_prompt"] = np.array(n_prompt, np.int32)
+        out[f"{name}.ts"] = ts
+    np.savez_compressed(os.path.join(HERE, "align_hf.npz"), **out)
+    print("align_hf.npz", {k: v.shape for k, v in out.items() if k.endswith(".ts")})
+
+
+def gen_logmel():
+    from transformers import WhisperFeatureExtractor
+    out = {}
+    for nm in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=nm)
+        out[f"filters{nm}"] = fe.mel_filters.astype(np.float32)
+        for name, wave in (("noise7s", H.noise(11, 7 * 16000)), ("speech30s", H.speechlike(12)),
+                           ("short1s", H.noise(13, 16000)), ("long31s", H.noise(14, 31 * 16000))):
+            r = fe(wave, sampling_rate=16000, return_tensors="np", return_attention_mask=True)
+            feats = r["input_features"][0]
+            out[f"{name}.{nm}.feats_sub"] = feats[:, ::7].copy()         # every 7th frame (file size)
+            out[f"{name}.{nm}.first"] = feats[:, :4].copy()
+            out[f"{name}.{nm}.last"] = feats[:, -4:].copy()
+            out[f"{name}.{nm}.frames"] = np.array(r["attention_mask"][0, ::160].sum() if r["attention_mask"].shape[1] == 480000
+                                                  else r["attention_mask"][0].sum(), np.int32)
+    np.savez_compressed(os.path.join(HERE, "logmel_hf.npz"), **out)
+    print("logmel_hf.npz", len(out))
+
+
+def gen_logits():
+    from transformers.generation.logits_process import (SuppressTokensAtBeginLogitsProcessor, SuppressTokensLogitsProcessor,
+                                                        WhisperTimeStampLogitsProcessor)
+
+    class GC:
+        pass
+    V = H.TOK_IDS["vocab"]
+    gc = GC()
+    gc.no_timestamps_token_id = H.TOK_IDS["no_timestamps"]
+    gc.eos_token_id = H.TOK_IDS["eos"]
+    gc.bos_token_id = H.TOK_IDS["eos"]
+    tsb = gc.no_timestamps_token_id + 1
+    histories = [
+        ([], None), ([], 50), ([tsb + 3], None), ([tsb + 3, 65], None), ([tsb + 3, 65, 66, tsb + 40], None),
+        ([tsb + 3, 65, tsb + 40, tsb + 40], None), ([tsb, 70, 71], None), ([tsb + 3, 65, tsb + 40, tsb + 40, 80], 50),
+        ([70, 71, 72], None), ([tsb + 1499], None),
+    ]
+    rng = np.random.default_rng(5)
+    out = {}
+    sup, bsup = [1, 2, 7, 300], [220, H.TOK_IDS["eos"]]
+    for i, (hist, mi) in enumerate(histories):
+        gc.max_initial_timestamp_index = mi
+        n_prompt = 3
+        ids = torch.tensor([[257, 258, 359] + hist])
+        for variant in range(2):
+            scores = torch.from_numpy((rng.standard_normal((1, V)) * (4.0 if variant == 0 else 0.5)).astype(np.float32))
+            if variant == 1:
+                scores[0, tsb:] += 2.0  # make the timestamp mass compete with the best text token
+            procs = [SuppressTokensAtBeginLogitsProcessor(bsup, n_prompt), SuppressTokensLogitsProcessor(sup),
+                     WhisperTimeStampLogitsProcessor(gc, begin_index=n_prompt)]
+            s = scores
+            for p in procs:
+                s = p(ids, s)
+            out[f"c{i}.{variant}.in"] = scores[0].numpy()
+            out[f"c{i}.{variant}.out"] = s[0].numpy()
+        out[f"c{i}.hist"] = np.array(hist, np.int64)
+        out[f"c{i}.mi"] = np.array(-1 if mi is None else mi, np.int64)
+    out["suppress"] = np.array(sup)
+    out["begin_suppress"] = np.array(bsup)
+    np.savez_compressed(os.path.join(HERE, "logits_hf.npz"), **out)
+    print("logits_hf.npz", len(out))
+
+
+def gen_pauses():
+    sys.path.insert(0, "/root/reference")
+    import utils as ref_utils  # REF/utils.py
+    cases = {
+        "empty": {"text": "", "chunks": []},
+        "single": {"text": "a", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}]},
+        "small_pause": {"text": "a b", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}, {"text": "b", "timestamp": (0.56, 1.0)}]},
+        "big_pause": {"text": "a b", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}, {"text": "b", "timestamp": (0.9, 1.0)}]},
+        "overlap": {"text": "a b", "chunks": [{"text": "a", "timestamp": (0.0, 0.6)}, {"text": "b", "timestamp": (0.5, 1.0)}]},
+        "zero": {"text": "a b", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}, {"text": "b", "timestamp": (0.5, 1.0)}]},
+        "chain": {"text": "a b c d", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}, {"text": "b", "timestamp": (0.54, 0.6)},
+                                               {"text": "c", "timestamp": (0.66, 1.2)}, {"text": "d", "timestamp": (2.0, 2.2)}]},
+        "exact_thr": {"text": "a b", "chunks": [{"text": "a", "timestamp": (0.0, 0.5)}, {"text": "b", "timestamp": (0.62, 1.0)}]},
+    }
+    out = {}
+    for k, v in cases.items():
+        for thr in (0.12, 0.3):
+            inp = copy.deepcopy(v)
+            res = ref_utils.adjust_pauses_for_hf_pipeline_output(copy.deepcopy(v), split_threshold=thr)
+            out[f"{k}@{thr}"] = {"input": inp, "output": res}
+    with open(os.path.join(HERE, "pauses_ref.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("pauses_ref.json", len(out))
+
+
+def gen_pipeline():
+    """cfg 1 / cfg 3 plumbing goldens: tiny random model + synthetic tokenizer through the reference's exact pipeline
+    call, then REF/utils.py."""
+    sys.path.insert(0, "/root/reference")
+    import utils as ref_utils
+    tok = H.synthetic_tokenizer()
+    out = {}
+    for name, n_mels, seed, wave, bs, max_new in (
+            ("clip5s", 128, 0, H.noise(0, 80000), 16, 40),
+            ("clip70s", 128, 1, np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)]), 16, 24),
+            ("clip70s_bs1", 128, 1, np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)]), 1, 24),
+            ("clip12s_80", 80, 2, H.speechlike(6, 12 * 16000), 2, 30)):
+        m = H.build_model(H.tiny_hf_config(n_mels=n_mels), seed=seed, logit_scale=4.0, max_new_tokens=max_new)
+        pipe = H.build_pipeline(m, tok, batch_size=bs)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = pipe(wave.copy())
+        adj = ref_utils.adjust_pauses_for_hf_pipeline_output(copy.deepcopy(res))
+        out[name] = {"n_mels": n_mels, "seed": seed, "batch_size": bs, "max_new_tokens": max_new, "logit_scale": 4.0,
+                     "pipeline": res, "adjusted": adj}
+        print(name, len(res["chunks"]), repr(res["text"][:60]))
+    with open(os.path.join(HERE, "pipeline_hf.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["align", "logmel", "logits", "pauses", "pipeline"]
+    for w in which:
+        globals()["gen_" + w]()
