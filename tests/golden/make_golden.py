@@ -170,20 +170,21 @@ def gen_pipeline():
     import utils as ref_utils
     tok = H.synthetic_tokenizer()
     out = {}
+    long70 = np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)])
     for name, n_mels, seed, wave, bs, max_new in (
             ("clip5s", 128, 0, H.noise(0, 80000), 16, 40),
-            ("clip70s", 128, 1, np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)]), 16, 24),
-            ("clip70s_bs1", 128, 1, np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)]), 1, 24),
+            ("clip70s", 128, 1, long70, 16, 24),
+            ("clip70s_bs1", 128, 1, long70, 1, 24),
             ("clip12s_80", 80, 2, H.speechlike(6, 12 * 16000), 2, 30)):
-        m = H.build_model(H.tiny_hf_config(n_mels=n_mels), seed=seed, logit_scale=4.0, max_new_tokens=max_new)
+        m = H.build_model(H.tiny_hf_config(n_mels=n_mels), seed=seed, logit_scale=8.0, pos_scale=20.0)
         pipe = H.build_pipeline(m, tok, batch_size=bs)
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            res = pipe(wave.copy())
+            res = pipe(wave.copy(), generate_kwargs={"max_new_tokens": max_new})
         adj = ref_utils.adjust_pauses_for_hf_pipeline_output(copy.deepcopy(res))
-        out[name] = {"n_mels": n_mels, "seed": seed, "batch_size": bs, "max_new_tokens": max_new, "logit_scale": 4.0,
-                     "pipeline": res, "adjusted": adj}
+        out[name] = {"n_mels": n_mels, "seed": seed, "batch_size": bs, "max_new_tokens": max_new, "logit_scale": 8.0,
+                     "pos_scale": 20.0, "pipeline": res, "adjusted": adj}
         print(name, len(res["chunks"]), repr(res["text"][:60]))
     with open(os.path.join(HERE, "pipeline_hf.json"), "w") as f:
         json.dump(out, f, indent=1)

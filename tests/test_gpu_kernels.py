@@ -132,7 +132,8 @@ def test_layernorm(engine):
         out = engine.layernorm(x, gm, bt)
         engine.sync()
         ref = torch.nn.functional.layer_norm(x, (d,), gm, bt, 1e-5)
-        assert (out.float() - ref).abs().max().item() < 3e-2
+        # bf16 output: half an ulp of the result (2^-9 relative) plus fp32 noise
+        assert ((out.float() - ref).abs() <= ref.abs() * 2 ** -8 + 2e-3).all()
 
 
 @pytest.mark.parametrize("B,S,H", [(1, 1500, 2), (2, 300, 3), (1, 64, 1), (2, 129, 2)])
