@@ -12,6 +12,7 @@ CW_OK = 0
 CW_DEC_SUPPRESS_EOS = 1
 CW_DEC_NO_TIMESTAMP_RULES = 2
 CW_DEC_NO_GRAPH = 4
+CW_DEC_PROFILE = 8
 
 # weight slot enums (must mirror include/crisper.h)
 W_GLOBAL = ["CONV1_W", "CONV1_B", "CONV2_W", "CONV2_B", "ENC_POS", "ENC_LNF_G", "ENC_LNF_B", "XKV_W", "XKV_B",
@@ -48,6 +49,7 @@ EXPORTS = {
     "cw_decode_greedy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cw_decode_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cw_align_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "cw_align": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -177,6 +177,12 @@ int cw_decode_greedy(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt,
                     argmax_out, steps_out_host, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int cw_decode_profile(const cw_ctx* ctx, double* ms_out, long long* n_out) {
+  CW_REQUIRE(ctx && ms_out && n_out, CW_ERR_INVALID, "cw_decode_profile: NULL argument");
+  for (int i = 0; i < 4; ++i) { ms_out[i] = ctx->prof_ms[i]; n_out[i] = ctx->prof_n[i]; }
+  return CW_OK;
+}
+
 size_t cw_align_workspace_bytes(int N, int T_max, int F_max) { return align_workspace_bytes(N, T_max, F_max); }
 
 int cw_align(cw_ctx* ctx, const float* align, const int32_t* T_len, const int32_t* F_len, int N, int H_a, int T_max,

@@ -70,4 +70,6 @@ struct cw_ctx {
   long long launches;
   void* gemm_state;      // gemm.cu private (tensor-map cache)
   void* dec_state;       // decoder.cu private (graph cache)
+  double prof_ms[4];     // CW_DEC_PROFILE accumulators
+  long long prof_n[4];
 };

@@ -19,6 +19,7 @@
 //   sample_kernel       suppress lists + timestamp rules + fp32 log-softmax rule + argmax + EOS bookkeeping
 // One decode step is captured once into a CUDA graph; the position lives in device memory, so the same graph is
 // replayed for every step (cudaGraphLaunch), with the host polling the "all finished" counter every 16 steps.
+#include <vector>
 #include "common.cuh"
 
 namespace cw {
@@ -572,6 +573,31 @@ size_t decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new) {
   return dec_layout(ctx->md, B, nullptr, nullptr);
 }
 
+// CW_DEC_PROFILE: one event after every kernel; consecutive differences are per-kernel device times.
+struct StepProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cat;
+  size_t used = 0;
+  cudaStream_t st = nullptr;
+  void mark(int category) {
+    if (!on) return;
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); cat.push_back(0); }
+    cat[used] = category;
+    cudaEventRecord(ev[used++], st);
+  }
+  void flush(cw_ctx* ctx) {  // call after a stream sync
+    for (size_t i = 1; i < used; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[i - 1], ev[i]) == cudaSuccess) { ctx->prof_ms[cat[i]] += ms; ctx->prof_n[cat[i]] += 1; }
+    }
+    used = 0;
+  }
+  ~StepProf() { for (auto e : ev) cudaEventDestroy(e); }
+};
+static thread_local StepProf* g_prof = nullptr;
+#define CW_PROF(catg) do { if (g_prof) g_prof->mark(catg); } while (0)
+
 template <int NT>
 static int launch_gemv(cw_ctx* ctx, int epi, const GemvParams& p, cudaStream_t st) {
   CW_REQUIRE(p.N % 16 == 0, CW_ERR_UNSUPPORTED, "gemv: N=%d must be a multiple of 16", p.N);
@@ -594,6 +620,7 @@ static int launch_gemv(cw_ctx* ctx, int epi, const GemvParams& p, cudaStream_t s
 #undef CW_GEMV_LAUNCH
   CW_CHECK_LAUNCH("gemv_kernel");
   ctx->launches += 1;
+  CW_PROF(0);
   return CW_OK;
 }
 
@@ -612,6 +639,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
                                   bf.x, d);
   CW_CHECK_LAUNCH("embed_kernel");
   ctx->launches += 1;
+  CW_PROF(3);
   const size_t cache_l = (size_t)B * m.n_text_ctx * d;
   const size_t xkv_l = (size_t)B * F * 2 * d;
   for (int l = 0; l < m.dec_layers; ++l) {
@@ -628,6 +656,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
                                                           d, m.n_text_ctx);
     CW_CHECK_LAUNCH("self_attn_kernel");
     ctx->launches += 1;
+    CW_PROF(1);
     memset(&g, 0, sizeof(g));
     g.W = (const bf16*)L[CW_DL_WO]; g.bias = (const float*)L[CW_DL_BO]; g.N = d; g.K = d; g.B = B;
     g.x_bf16 = bf.attn; g.out_f32 = bf.x; g.st = bf.st;
@@ -643,6 +672,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
                                                                  m.n_align_heads, max_new, n_prompt, d, F);
     CW_CHECK_LAUNCH("cross_attn_kernel");
     ctx->launches += 1;
+    CW_PROF(2);
     memset(&g, 0, sizeof(g));
     g.W = (const bf16*)L[CW_DL_WOC]; g.bias = (const float*)L[CW_DL_BOC]; g.N = d; g.K = d; g.B = B;
     g.x_bf16 = bf.attn; g.out_f32 = bf.x; g.st = bf.st;
@@ -661,6 +691,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   ln_rows_kernel<<<B, 256, 0, st>>>(bf.x, (const float*)W[CW_W_DEC_LNF_G], (const float*)W[CW_W_DEC_LNF_B], bf.xn, d);
   CW_CHECK_LAUNCH("ln_rows_kernel");
   ctx->launches += 1;
+  CW_PROF(3);
   GemvParams g;
   memset(&g, 0, sizeof(g));
   g.W = (const bf16*)W[CW_W_TOK_EMB]; g.bias = nullptr; g.N = m.vocab_padded; g.K = d; g.B = B;
@@ -676,6 +707,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   advance_kernel<<<1, 1, 0, st>>>(bf.st);
   CW_CHECK_LAUNCH("advance_kernel");
   ctx->launches += 2;
+  CW_PROF(3);
   return CW_OK;
 }
 
@@ -727,7 +759,11 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
 
   const int total_steps = n_prompt - 1 + max_new;  // positions 0 .. n_prompt+max_new-2
   // stream capture is not available on the legacy / per-thread default streams
-  const bool use_graph = !(flags & CW_DEC_NO_GRAPH) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  const bool profile = (flags & CW_DEC_PROFILE) != 0;
+  StepProf prof;
+  prof.on = profile; prof.st = st;
+  if (profile) { for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; } }
+  const bool use_graph = !(flags & (CW_DEC_NO_GRAPH | CW_DEC_PROFILE)) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   int rc = CW_OK;
   DecGraph* G = (DecGraph*)ctx->dec_state;
   if (use_graph) {
@@ -763,8 +799,11 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       CW_CUDA(cudaGraphLaunch(G->exec, st));
       ctx->launches += per_step;
     } else {
+      if (profile) { g_prof = &prof; prof.mark(3); }
       rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+      g_prof = nullptr;
       if (rc != CW_OK) return rc;
+      if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
     }
     if (s >= n_prompt - 1) steps_done = s - (n_prompt - 1) + 1;
     const bool poll = !(flags & CW_DEC_SUPPRESS_EOS) && forced == nullptr && ((s & 15) == 15);

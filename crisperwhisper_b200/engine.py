@@ -177,6 +177,13 @@ class Engine:
                                               _p(ws), ws.numel(), self._sp()), "cw_decode_greedy")
         return dict(tokens=tokens, lengths=lens, align=align, logits=logits, argmax=argmax, steps=steps.value)
 
+    def decode_profile(self):
+        """(ms[4], launches[4]) of the last CW_DEC_PROFILE decode: gemv, self-attn, cross-attn, other."""
+        ms = (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
+        L.check(self.lib.cw_decode_profile(self._h, ms, n), "cw_decode_profile")
+        return list(ms), list(n)
+
     # -- stage 3 -----------------------------------------------------------------------------------------
     def align(self, align: torch.Tensor, T_len: torch.Tensor, F_len: torch.Tensor, median_width: int = 7) -> torch.Tensor:
         """align f32 [N, H, T_max, F_max]; T_len/F_len i32 [N] -> jump index i32 [N, T_max]."""

@@ -164,6 +164,8 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
                 stats["decode_steps"] = stats.get("decode_steps", 0) + out["steps"]
             toks_g = out["tokens"].cpu().numpy()
             gen_counts = out["lengths"].cpu().numpy() - n_prompt   # generated tokens incl. eos
+            if stats is not None:
+                stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + toks_g.nbytes + gen_counts.nbytes
             G_g = int(gen_counts.max())                             # HF: the batch decodes until its longest row ends
             # alignment rows = G - 1: the last generated token is never fed back (generation_whisper.py:371-376)
             T_rows = np.full(nb, G_g - 1) if opts.hf_batch_compat else gen_counts - 1
@@ -174,6 +176,8 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
                                  torch.from_numpy(np.maximum(F_len, 1).astype(np.int32)), cfg["median_filter_width"])
                 engine.sync()
                 jump_g = j.cpu().numpy()
+                if stats is not None:
+                    stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + jump_g.nbytes
             else:
                 jump_g = np.zeros((nb, max_new), np.int32)
             toks_l.append(toks_g); G_l += [G_g] * nb; T_l += T_rows.tolist(); jump_l.append(jump_g)

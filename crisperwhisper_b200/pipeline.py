@@ -88,53 +88,56 @@ class AutomaticSpeechRecognitionPipeline:
     # ------------------------------------------------------------------------------------------------------
     def __call__(self, inputs, return_timestamps=None, generate_kwargs: Optional[Dict] = None, batch_size=None,
                  chunk_length_s=None, **kw):
-        if isinstance(inputs, (list, tuple)) and not isinstance(inputs, (str, bytes)):
-            return [self(x, return_timestamps=return_timestamps, generate_kwargs=generate_kwargs, batch_size=batch_size,
-                         chunk_length_s=chunk_length_s) for x in inputs]
+        """Single input -> dict; list of inputs -> list of dicts.  Like HF's DataLoader-backed pipeline, chunks of
+        different inputs share batches of `batch_size` (HF/pipelines/base.py:1298-1318)."""
+        is_list = isinstance(inputs, (list, tuple))
+        items = list(inputs) if is_list else [inputs]
         rt = return_timestamps if return_timestamps is not None else self.return_timestamps
         gk = dict(self.generate_kwargs)
         gk.update(generate_kwargs or {})
         bs = self.batch_size if batch_size is None else max(1, int(batch_size))
         cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
-        wave = A.normalize_input(inputs)
-        model_outputs = self._run(wave, cl, bs, gk)
-        return self._postprocess(model_outputs, rt)
+        waves = [A.normalize_input(x) for x in items]
+        per_input = self._run(waves, cl, bs, gk)
+        results = [self._postprocess(mo, rt) for mo in per_input]
+        return results if is_list else results[0]
 
     # ------------------------------------------------------------------------------------------------------
-    def _run(self, wave: np.ndarray, chunk_length_s, batch_size: int, gk: Dict) -> List[Dict]:
+    def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict) -> List[List[Dict]]:
         eng = self.engine
-        if chunk_length_s:
-            plan = A.chunk_plan(len(wave), chunk_length_s, self.stride_length_s)
-            with_stride = True
-        else:
-            if len(wave) > A.N_SAMPLES:
-                raise NotImplementedError("inputs longer than 30 s need chunk_length_s (the reference always sets 30)")
-            plan = [(0, len(wave), 0, 0, True)]
-            with_stride = False
+        plan = []  # (input index, start, length, left, right, is_last, with_stride)
+        for wi, wave in enumerate(waves):
+            if chunk_length_s:
+                plan += [(wi,) + p + (True,) for p in A.chunk_plan(len(wave), chunk_length_s, self.stride_length_s)]
+            else:
+                if len(wave) > A.N_SAMPLES:
+                    raise NotImplementedError("inputs longer than 30 s need chunk_length_s (the reference always sets 30)")
+                plan.append((wi, 0, len(wave), 0, 0, True, False))
         opts = G.GenOptions(max_new_tokens=gk.get("max_new_tokens"), max_length=gk.get("max_length", 448),
                             hf_batch_compat=gk.get("hf_batch_compat", self.hf_batch_compat),
                             force_unique_generate_call=bool(gk.get("force_unique_generate_call", False)),
                             suppress_eos=bool(gk.get("suppress_eos", False)), init_tokens=gk.get("init_tokens"))
-        stats = {"chunks": len(plan), "decode_steps": 0, "generate_passes": 0}
-        outputs: List[Dict] = []
+        stats = {"chunks": len(plan), "decode_steps": 0, "generate_passes": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        outputs: List[List[Dict]] = [[] for _ in waves]
         for b0 in range(0, len(plan), batch_size):
             items = plan[b0:b0 + batch_size]
             host = torch.zeros(len(items), A.N_SAMPLES, dtype=torch.float32, pin_memory=True)
             n_valid = []
-            for k, (start, length, _, _, _) in enumerate(items):
+            for k, (wi, start, length, _, _, _, _) in enumerate(items):
                 n = min(length, A.N_SAMPLES)
-                host[k, :n] = torch.from_numpy(wave[start:start + n])
+                host[k, :n] = torch.from_numpy(waves[wi][start:start + n])
                 n_valid.append(n)
             dev_wave = host.to(eng.device, non_blocking=True)
+            stats["h2d_bytes"] += host.numel() * 4
             nv = torch.tensor(n_valid, dtype=torch.int32, device=eng.device)
             _, tm, frames = eng.logmel(dev_wave, self.mel_filters, nv, want_f32=False, want_tm=True)
             eng.sync()
             res = G.generate(eng, tm, frames.cpu().numpy(), opts, stats)
-            for (start, length, left, right, is_last), r in zip(items, res):
+            for (wi, start, length, left, right, is_last, with_stride), r in zip(items, res):
                 out = {"tokens": r["tokens"][None, :], "token_timestamps": [r["token_timestamps"].tolist()], "is_last": is_last}
                 if with_stride:
                     out["stride"] = (length, left, right)
-                outputs.append(out)
+                outputs[wi].append(out)
         self.last_stats = stats
         return outputs
 

@@ -186,11 +186,17 @@ int cw_encode(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xkv
 #define CW_DEC_SUPPRESS_EOS 1     /* never pick eos (fixed-length benchmark decode) */
 #define CW_DEC_NO_TIMESTAMP_RULES 2 /* skip WhisperTimeStampLogitsProcessor (return_timestamps=False) */
 #define CW_DEC_NO_GRAPH 4         /* launch kernels directly instead of replaying a captured CUDA graph */
+#define CW_DEC_PROFILE 8          /* direct launches with a CUDA event after every kernel; read with cw_decode_profile */
 size_t cw_decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new);
 int cw_decode_greedy(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n_prompt, int max_new,
                      int flags, const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out,
                      float* logits_out, int32_t* argmax_out, int* steps_out_host, void* ws, size_t ws_bytes,
                      void* stream);
+
+/* Per-category device time of the most recent CW_DEC_PROFILE decode (CUDA events on the launching stream):
+ * categories 0 = weight-streaming GEMV kernels, 1 = self-attention, 2 = cross-attention, 3 = everything else.
+ * ms_out[4] accumulated milliseconds, n_out[4] number of launches. */
+int cw_decode_profile(const cw_ctx* ctx, double* ms_out, long long* n_out);
 
 /* ---- stage 3: token timestamps (replaces WhisperGenerationMixin._extract_token_timestamps,
  *      _median_filter and _dynamic_time_warping, HF/models/whisper/generation_whisper.py:241-381,43-61,64-115) --
