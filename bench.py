@@ -206,7 +206,7 @@ def main():
     from crisperwhisper_b200 import generate as G
     from crisperwhisper_b200 import weights as Wt
     from crisperwhisper_b200.engine import Engine
-    from crisperwhisper_b200.pipeline import mel_filters_slaney, pipeline
+    from crisperwhisper_b200.asr_pipeline import mel_filters_slaney, pipeline
 
     eng = Engine(local_rank)
     dev = eng.device

@@ -8,7 +8,7 @@ __all__ = ["pipeline", "adjust_pauses_for_hf_pipeline_output", "Engine"]
 
 def __getattr__(name):  # lazy: importing the package must not need torch/CUDA (build() runs on a CPU box)
     if name == "pipeline":
-        from .pipeline import pipeline
+        from .asr_pipeline import pipeline
         return pipeline
     if name == "Engine":
         from .engine import Engine

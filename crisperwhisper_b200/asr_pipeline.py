@@ -134,7 +134,7 @@ class AutomaticSpeechRecognitionPipeline:
             eng.sync()
             res = G.generate(eng, tm, frames.cpu().numpy(), opts, stats)
             for (wi, start, length, left, right, is_last, with_stride), r in zip(items, res):
-                out = {"tokens": r["tokens"][None, :], "token_timestamps": [r["token_timestamps"].tolist()], "is_last": is_last}
+                out = {"tokens": r["tokens"][None, :], "token_timestamps": r["token_timestamps"][None, :], "is_last": is_last}
                 if with_stride:
                     out["stride"] = (length, left, right)
                 outputs[wi].append(out)

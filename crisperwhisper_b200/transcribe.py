@@ -10,7 +10,7 @@ import sys
 def transcribe_audio(file_path, model_id="nyrahealth/CrisperWhisper"):
     import torch
     from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
-    from .pipeline import pipeline
+    from .asr_pipeline import pipeline
     from .utils import adjust_pauses_for_hf_pipeline_output
 
     if not torch.cuda.is_available():

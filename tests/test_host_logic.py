@@ -66,7 +66,7 @@ def test_retrieve_segment_matches_hf(seq):
 
 def test_mel_filters_match_hf():
     from transformers import WhisperFeatureExtractor
-    from crisperwhisper_b200.pipeline import mel_filters_slaney
+    from crisperwhisper_b200.asr_pipeline import mel_filters_slaney
     for nm in (80, 128):
         ref = WhisperFeatureExtractor(feature_size=nm).mel_filters.T.astype(np.float32)
         assert np.array_equal(mel_filters_slaney(nm), ref)
