@@ -76,31 +76,70 @@ __global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
 
   // ---- phase 0: activations -> bf16 rows in smem (LayerNorm fused when requested) -------------------------
   if (p.ln_g != nullptr) {
+    // one warp per sample row; the whole row (K <= 1280 floats) lives in registers so every load is in flight at once
+    const int nv = K >> 7;  // float4 per lane
     for (int b = warp; b < 8 * NT; b += nwarps) {
       bf16* dst = xs + (size_t)b * XS;
       if (b < p.B) {
-        const float* xr = p.x_f32 + (size_t)b * K;
+        const float4* xr = reinterpret_cast<const float4*>(p.x_f32 + (size_t)b * K);
+        float4 v[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) v[i] = (i < nv) ? xr[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
         float s = 0.f;
-        for (int k = lane; k < K; k += 32) s += xr[k];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float mean = s / (float)K;
         float q = 0.f;
-        for (int k = lane; k < K; k += 32) { float dd = xr[k] - mean; q += dd * dd; }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          if (i < nv) {
+            float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+            q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+          }
+        }
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         const float rstd = rsqrtf(q / (float)K + 1e-5f);
-        for (int k = lane; k < K; k += 32)
-          dst[k] = __float2bfloat16((xr[k] - mean) * rstd * __ldg(p.ln_g + k) + __ldg(p.ln_b + k));
+        const float4* g4 = reinterpret_cast<const float4*>(p.ln_g);
+        const float4* b4 = reinterpret_cast<const float4*>(p.ln_b);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          if (i < nv) {
+            const float4 g = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(dst + 4 * (lane + 32 * i)) = u;
+          }
+        }
       } else {
         for (int k = lane; k < K; k += 32) dst[k] = __float2bfloat16(0.f);
       }
     }
   } else {
     const int vec_per_row = K >> 3;
-    for (int i = tid; i < 8 * NT * vec_per_row; i += blockDim.x) {
-      int b = i / vec_per_row, c = i - b * vec_per_row;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (b < p.B) v = *reinterpret_cast<const uint4*>(p.x_bf16 + (size_t)b * K + c * 8);
-      *reinterpret_cast<uint4*>(xs + (size_t)b * XS + c * 8) = v;
+    const int total = 8 * NT * vec_per_row;
+    for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        v[u] = make_uint4(0, 0, 0, 0);
+        if (i < total) {
+          const int b = i / vec_per_row, c = i - b * vec_per_row;
+          if (b < p.B) v[u] = *reinterpret_cast<const uint4*>(p.x_bf16 + (size_t)b * K + c * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          const int b = i / vec_per_row, c = i - b * vec_per_row;
+          *reinterpret_cast<uint4*>(xs + (size_t)b * XS + c * 8) = v[u];
+        }
+      }
     }
   }
   __syncthreads();
@@ -213,66 +252,135 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// causal self-attention for one new token: grid (n_heads, B), 128 threads
-// q f32 [B, d] (pre-scaled), caches bf16 [B, n_ctx, d]; out bf16 [B, d]
+// Decode attention (one query row per (sample, head)) over `n` key/value rows of 64 bf16 each.
+// Mapping: 8 threads per row (16 B each), kThreads/8 rows per pass, UN passes unrolled so that every thread keeps
+// UN 16-byte loads in flight (these kernels are pure HBM/L2 latency otherwise).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) self_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kc,
-                                                       const bf16* __restrict__ vc, bf16* __restrict__ out,
-                                                       const DecState* st, int d, int n_ctx) {
-  __shared__ float sq[64];
-  __shared__ float sp[448];
-  __shared__ float sred[4];
-  __shared__ float so[2][64];
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int n = st->pos + 1;  // keys 0..pos
-  if (tid < 64) sq[tid] = q[(size_t)b * d + h * 64 + tid];
-  __syncthreads();
-  const bf16* kb = kc + (size_t)b * n_ctx * d + h * 64;
-  const bf16* vb = vc + (size_t)b * n_ctx * d + h * 64;
-  float lmax = -INFINITY;
-  for (int j = tid; j < n; j += 128) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * d);
-    float s = 0.f;
+__device__ __forceinline__ float dot8(const uint4& u, const float* qv) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+  float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint4 u = kr[c];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h2[e]);
-        s = fmaf(sq[c * 8 + 2 * e], f.x, s);
-        s = fmaf(sq[c * 8 + 2 * e + 1], f.y, s);
-      }
-    }
-    sp[j] = s;
-    lmax = fmaxf(lmax, s);
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __bfloat1622float2(h2[e]);
+    s = fmaf(qv[2 * e], f.x, s);
+    s = fmaf(qv[2 * e + 1], f.y, s);
   }
+  return s;
+}
+
+template <int kThreads, int UN, int kMaxN>
+__device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const bf16* __restrict__ kb, const bf16* __restrict__ vb,
+                                            size_t row_stride, int n, float* sq, float* sp, float* sred, float (*so)[65],
+                                            bf16* __restrict__ out64, float* prob_dst) {
+  constexpr int G = kThreads / 8;
+  const int tid = threadIdx.x, sub = tid & 7, grp = tid >> 3;
+  if (tid < 64) sq[tid] = q64[tid];
+  __syncthreads();
+  float qv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e];
+  // scores
+  for (int j0 = grp; j0 < n; j0 += G * UN) {
+    uint4 u[UN];
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = j0 + G * x;
+      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+    }
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = j0 + G * x;
+      float s = (j < n) ? dot8(u[x], qv) : 0.f;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (sub == 0 && j < n) sp[j] = s;
+    }
+  }
+  __syncthreads();
+  float lmax = -INFINITY;
+  for (int j = tid; j < n; j += kThreads) lmax = fmaxf(lmax, sp[j]);
   for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
   if ((tid & 31) == 0) sred[tid >> 5] = lmax;
   __syncthreads();
-  const float mx = fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3]));
+  float mx = sred[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w) mx = fmaxf(mx, sred[w]);
   __syncthreads();
   float lsum = 0.f;
-  for (int j = tid; j < n; j += 128) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
+  for (int j = tid; j < n; j += kThreads) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   if ((tid & 31) == 0) sred[tid >> 5] = lsum;
   __syncthreads();
-  const float inv = 1.f / (sred[0] + sred[1] + sred[2] + sred[3]);
-  // out[dd] = sum_j p[j] v[j][dd]; two halves of the keys
-  const int dd = tid & 63, half = tid >> 6;
-  float acc = 0.f;
-  for (int j = half; j < n; j += 2) acc = fmaf(sp[j], __bfloat162float(vb[(size_t)j * d + dd]), acc);
-  so[half][dd] = acc;
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) tot += sred[w];
+  const float inv = 1.f / tot;
+  for (int j = tid; j < n; j += kThreads) {
+    const float pj = sp[j] * inv;
+    sp[j] = pj;
+    if (prob_dst) prob_dst[j] = pj;
+  }
   __syncthreads();
-  if (tid < 64) out[(size_t)b * d + h * 64 + tid] = __float2bfloat16((so[0][tid] + so[1][tid]) * inv);
+  // out = sum_j p[j] * V[j]
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j0 = grp; j0 < n; j0 += G * UN) {
+    uint4 u[UN];
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = j0 + G * x;
+      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
+    }
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = j0 + G * x;
+      if (j < n) {
+        const float pj = sp[j];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[x]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+          acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) so[grp][sub * 8 + e] = acc[e];
+  __syncthreads();
+  if (tid < 64) {
+    float v = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < G; ++r) v += so[r][tid];
+    out64[tid] = __float2bfloat16(v);
+  }
+  (void)kMaxN;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// cross-attention for one new token over F encoder frames: grid (n_heads, B), 256 threads
+// causal self-attention for one new token: grid (n_heads, B); q f32 [B, d] (pre-scaled), caches bf16 [B, n_ctx, d]
+static constexpr int kSThreads = 128;
+__global__ void __launch_bounds__(kSThreads) self_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kc,
+                                                             const bf16* __restrict__ vc, bf16* __restrict__ out,
+                                                             const DecState* st, int d, int n_ctx) {
+  __shared__ float sq[64];
+  __shared__ float sp[448];
+  __shared__ float sred[kSThreads / 32];
+  __shared__ float so[kSThreads / 8][65];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int n = st->pos + 1;  // keys 0..pos
+  const bf16* kb = kc + (size_t)b * n_ctx * d + h * 64;
+  const bf16* vb = vc + (size_t)b * n_ctx * d + h * 64;
+  attend_rows<kSThreads, 4, 448>(q + (size_t)b * d + h * 64, kb, vb, (size_t)d, n, sq, sp, sred, so,
+                                 out + (size_t)b * d + h * 64, nullptr);
+}
+
+// cross-attention for one new token over F encoder frames: grid (n_heads, B)
 // xkv layer slice: bf16 [B, F, 2, n_heads, 64];  q f32 [B, d] (pre-scaled);  out bf16 [B, d]
 // align_out f32 [B, H_a, T_cap, F]: row s = pos - n_prompt of slot align_map[h] gets the probabilities
-// ---------------------------------------------------------------------------------------------------------
-static constexpr int kXThreads = 256;
+static constexpr int kXThreads = 512;
 static constexpr int kFMax = 1500;
 
 __global__ void __launch_bounds__(kXThreads) cross_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ xkv,
@@ -281,86 +389,19 @@ __global__ void __launch_bounds__(kXThreads) cross_attn_kernel(const float* __re
                                                               int H_a, int T_cap, int n_prompt, int d, int F) {
   __shared__ float sq[64];
   __shared__ float sp[kFMax];
-  __shared__ float sred[8];
-  __shared__ float so[32][65];
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int n_heads = d >> 6;
-  if (tid < 64) sq[tid] = q[(size_t)b * d + h * 64 + tid];
-  __syncthreads();
+  __shared__ float sred[kXThreads / 32];
+  __shared__ float so[kXThreads / 8][65];
+  const int h = blockIdx.x, b = blockIdx.y;
   const size_t fstride = (size_t)2 * d;  // elements per frame (K | V)
   const bf16* kb = xkv + (size_t)b * F * fstride + h * 64;
   const bf16* vb = kb + d;
-  float lmax = -INFINITY;
-  for (int j = tid; j < F; j += kXThreads) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * fstride);
-    uint4 u[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) u[c] = ldg_stream(kr + c);
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[c]);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float2 f = __bfloat1622float2(h2[e]);
-        s = fmaf(sq[c * 8 + 2 * e], f.x, s);
-        s = fmaf(sq[c * 8 + 2 * e + 1], f.y, s);
-      }
-    }
-    sp[j] = s;
-    lmax = fmaxf(lmax, s);
-  }
-  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  if ((tid & 31) == 0) sred[tid >> 5] = lmax;
-  __syncthreads();
-  float mx = sred[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sred[w]);
-  __syncthreads();
-  float lsum = 0.f;
-  for (int j = tid; j < F; j += kXThreads) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
-  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  if ((tid & 31) == 0) sred[tid >> 5] = lsum;
-  __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) tot += sred[w];
-  const float inv = 1.f / tot;
-  // normalised probabilities (needed both for the output and for the alignment rows)
-  for (int j = tid; j < F; j += kXThreads) sp[j] *= inv;
-  __syncthreads();
   const int slot = align_map_layer[h];
   const int s_row = st->pos - n_prompt;
-  if (slot >= 0 && s_row >= 0 && s_row < T_cap && align_out != nullptr) {
-    float* dst = align_out + (((size_t)b * H_a + slot) * T_cap + s_row) * F;
-    for (int j = tid; j < F; j += kXThreads) dst[j] = sp[j];
-  }
-  // out[dd] = sum_j p[j] V[j][dd]: 8 threads per frame row (16 B each), 32 frame rows in flight
-  const int sub = tid & 7, grp = tid >> 3;
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int j = grp; j < F; j += 32) {
-    uint4 u = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * fstride) + sub);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
-    const float pj = sp[j];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __bfloat1622float2(h2[e]);
-      acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
-      acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) so[grp][sub * 8 + e] = acc[e];
-  __syncthreads();
-  if (tid < 64) {
-    float v = 0.f;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) v += so[r][tid];
-    out[(size_t)b * d + h * 64 + tid] = __float2bfloat16(v);
-  }
-  (void)n_heads;
+  float* prob_dst = nullptr;
+  if (slot >= 0 && s_row >= 0 && s_row < T_cap && align_out != nullptr)
+    prob_dst = align_out + (((size_t)b * H_a + slot) * T_cap + s_row) * F;
+  attend_rows<kXThreads, 8, kFMax>(q + (size_t)b * d + h * 64, kb, vb, fstride, F, sq, sp, sred, so,
+                                   out + (size_t)b * d + h * 64, prob_dst);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -522,6 +563,14 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
 
 __global__ void advance_kernel(DecState* st) { st->pos += 1; }
 
+// CW_DEC_PROFILE: keeps the GPU busy while the host queues the profiled launches, so that the event timestamps
+// bracket kernels that run back to back instead of host launch latency.
+__global__ void spin_kernel(long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while ((long long)(t - t0) < ns);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -605,6 +654,7 @@ static int launch_gemv(cw_ctx* ctx, int epi, const GemvParams& p, cudaStream_t s
   CW_REQUIRE(nwarps > 0, CW_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 128", p.K);
   size_t smem = (size_t)8 * NT * (p.K + 32) * 2 + (size_t)nwarps * 16 * 8 * NT * 4;
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "gemv: smem %zu too large (K=%d)", smem, p.K);
+  CW_REQUIRE(p.ln_g == nullptr || p.K <= 1280, CW_ERR_UNSUPPORTED, "gemv: fused LayerNorm needs K=%d <= 1280", p.K);
   dim3 grid(p.N / 16), block(nwarps * 32);
 #define CW_GEMV_LAUNCH(E)                                                                                         \
   {                                                                                                               \
@@ -652,7 +702,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
     g.out_f32 = bf.qbuf; g.kcache = bf.kc + l * cache_l; g.vcache = bf.vc + l * cache_l; g.d = d; g.n_ctx = m.n_text_ctx;
     g.st = bf.st;
     if ((rc = gemv(ctx, B, EPI_QKV, g, st)) != CW_OK) return rc;
-    self_attn_kernel<<<dim3(m.n_heads, B), 128, 0, st>>>(bf.qbuf, bf.kc + l * cache_l, bf.vc + l * cache_l, bf.attn, bf.st,
+    self_attn_kernel<<<dim3(m.n_heads, B), kSThreads, 0, st>>>(bf.qbuf, bf.kc + l * cache_l, bf.vc + l * cache_l, bf.attn, bf.st,
                                                           d, m.n_text_ctx);
     CW_CHECK_LAUNCH("self_attn_kernel");
     ctx->launches += 1;
@@ -794,6 +844,12 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   const long long per_step = 5 + 8LL * m.dec_layers;  // kernels in one step
   int steps_done = 0;  // generated tokens
   int h_state[4] = {0, 0, 0, 0};
+  if (profile) {
+    long long ns = (long long)total_steps * 3000000LL;  // ~3 ms of head start per step for the host
+    if (ns > 400000000LL) ns = 400000000LL;
+    spin_kernel<<<1, 1, 0, st>>>(ns);
+    CW_CHECK_LAUNCH("spin_kernel");
+  }
   for (int s = 0; s < total_steps; ++s) {
     if (use_graph) {
       CW_CUDA(cudaGraphLaunch(G->exec, st));
@@ -803,7 +859,6 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
       g_prof = nullptr;
       if (rc != CW_OK) return rc;
-      if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
     }
     if (s >= n_prompt - 1) steps_done = s - (n_prompt - 1) + 1;
     const bool poll = !(flags & CW_DEC_SUPPRESS_EOS) && forced == nullptr && ((s & 15) == 15);
@@ -813,6 +868,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       if (h_state[1] >= B) break;
     }
   }
+  if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
   dec_finish_kernel<<<B, 128, 0, st>>>(bf.seq, m.n_text_ctx, n_prompt, n_prompt + max_new, m.eos_id, tokens_out, len_out, B,
                                        steps_done);
   CW_CHECK_LAUNCH("dec_finish_kernel");
