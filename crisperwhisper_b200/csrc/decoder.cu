@@ -280,11 +280,14 @@ __device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const
 #pragma unroll
   for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e];
   // scores
-  for (int j0 = grp; j0 < n; j0 += G * UN) {
+  // NB: the loop bounds are block-uniform (the shuffles below need every lane of the warp)
+  for (int base = 0; base < n; base += G * UN) {
+    const int j0 = base + grp;
     uint4 u[UN];
 #pragma unroll
     for (int x = 0; x < UN; ++x) {
       const int j = j0 + G * x;
+      u[x] = make_uint4(0, 0, 0, 0);
       if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
     }
 #pragma unroll
@@ -326,11 +329,13 @@ __device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int j0 = grp; j0 < n; j0 += G * UN) {
+  for (int base = 0; base < n; base += G * UN) {
+    const int j0 = base + grp;
     uint4 u[UN];
 #pragma unroll
     for (int x = 0; x < UN; ++x) {
       const int j = j0 + G * x;
+      u[x] = make_uint4(0, 0, 0, 0);
       if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
     }
 #pragma unroll
