@@ -51,6 +51,26 @@ struct GemvParams {
   const DecState* st;
 };
 
+// Programmatic dependent launch (PDL): every decode kernel lets its successor start launching right away and waits
+// for its predecessor only after it has issued the loads that do not depend on it (weights, encoder K/V).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool g_use_pdl = true;
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -73,6 +93,25 @@ __global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
   float* red = reinterpret_cast<float*>(gsm + (size_t)8 * NT * XS * 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
+  pdl_trigger();
+  // weights do not depend on the previous kernel: get the first U chunks of this warp's K-slice in flight now
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  const int kslice = K / nwarps;        // multiple of 32 (checked on the host)
+  const int kbeg = warp * kslice;
+  const int chunks = kslice >> 5;
+  const bf16* w0 = p.W + (size_t)(n0 + g) * K + kbeg + 8 * t;
+  const bf16* w1 = w0 + (size_t)8 * K;
+  constexpr int U = 5;
+  uint4 a0[U], a1[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < chunks) {
+      a0[u] = ldg_stream(w0 + (size_t)u * 32);
+      a1[u] = ldg_stream(w1 + (size_t)u * 32);
+    }
+  }
+  pdl_wait();
 
   // ---- phase 0: activations -> bf16 rows in smem (LayerNorm fused when requested) -------------------------
   if (p.ln_g != nullptr) {
@@ -145,24 +184,17 @@ __global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
   __syncthreads();
 
   // ---- phase 1: 16 output rows per CTA, K split across warps ---------------------------------------------
-  const int g = lane >> 2, t = lane & 3;
-  const int n0 = blockIdx.x * 16;
-  const int kslice = K / nwarps;        // multiple of 32 (checked on the host)
-  const int kbeg = warp * kslice;
-  const int chunks = kslice >> 5;
-  const bf16* w0 = p.W + (size_t)(n0 + g) * K + kbeg + 8 * t;
-  const bf16* w1 = w0 + (size_t)8 * K;
   float acc[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-  constexpr int U = 5;
   for (int c0 = 0; c0 < chunks; c0 += U) {
-    uint4 a0[U], a1[U];
+    if (c0 > 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (c0 + u < chunks) {
-        a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
-        a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+      for (int u = 0; u < U; ++u) {
+        if (c0 + u < chunks) {
+          a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+          a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+        }
       }
     }
 #pragma unroll
@@ -216,6 +248,8 @@ __global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const bf16* __restrict__ emb, const float* __restrict__ pos_tab, const int* __restrict__ seq,
                              int seq_ld, const DecState* st, float* __restrict__ x, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int pos = st->pos;
   const int tok = seq[(size_t)b * seq_ld + pos];
@@ -227,6 +261,8 @@ __global__ void embed_kernel(const bf16* __restrict__ emb, const float* __restri
 // LayerNorm of B rows f32 -> bf16 (final decoder norm before proj_out, modeling_whisper.py:791)
 __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                                bf16* __restrict__ out, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const float* xr = x + (size_t)b * d;
   __shared__ float sh[32];
@@ -268,12 +304,29 @@ __device__ __forceinline__ float dot8(const uint4& u, const float* qv) {
   return s;
 }
 
-template <int kThreads, int UN, int kMaxN>
+template <int kThreads, int UN, int kMaxN, bool kPrefetchK>
 __device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const bf16* __restrict__ kb, const bf16* __restrict__ vb,
                                             size_t row_stride, int n, float* sq, float* sp, float* sred, float (*so)[65],
-                                            bf16* __restrict__ out64, float* prob_dst) {
+                                            bf16* __restrict__ out64, float* prob_rows, const DecState* st, int n_prompt,
+                                            int T_cap) {
   constexpr int G = kThreads / 8;
   const int tid = threadIdx.x, sub = tid & 7, grp = tid >> 3;
+  pdl_trigger();
+  uint4 u0[UN];
+  if (kPrefetchK) {  // K rows of the encoder are read-only during decoding: issue the first pass before the wait
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = grp + G * x;
+      u0[x] = make_uint4(0, 0, 0, 0);
+      if (j < n) u0[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+    }
+  }
+  pdl_wait();
+  float* prob_dst = nullptr;  // alignment head: row s = pos - n_prompt of this (sample, slot) receives the probabilities
+  if (prob_rows != nullptr) {
+    const int s_row = st->pos - n_prompt;
+    if (s_row >= 0 && s_row < T_cap) prob_dst = prob_rows + (size_t)s_row * n;
+  }
   if (tid < 64) sq[tid] = q64[tid];
   __syncthreads();
   float qv[8];
@@ -288,7 +341,8 @@ __device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const
     for (int x = 0; x < UN; ++x) {
       const int j = j0 + G * x;
       u[x] = make_uint4(0, 0, 0, 0);
-      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+      if (kPrefetchK && base == 0) u[x] = u0[x];
+      else if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
     }
 #pragma unroll
     for (int x = 0; x < UN; ++x) {
@@ -375,11 +429,12 @@ __global__ void __launch_bounds__(kSThreads) self_attn_kernel(const float* __res
   __shared__ float sred[kSThreads / 32];
   __shared__ float so[kSThreads / 8][65];
   const int h = blockIdx.x, b = blockIdx.y;
+  pdl_wait();  // pos and the cache row of this step come from the previous kernels
   const int n = st->pos + 1;  // keys 0..pos
   const bf16* kb = kc + (size_t)b * n_ctx * d + h * 64;
   const bf16* vb = vc + (size_t)b * n_ctx * d + h * 64;
-  attend_rows<kSThreads, 4, 448>(q + (size_t)b * d + h * 64, kb, vb, (size_t)d, n, sq, sp, sred, so,
-                                 out + (size_t)b * d + h * 64, nullptr);
+  attend_rows<kSThreads, 4, 448, false>(q + (size_t)b * d + h * 64, kb, vb, (size_t)d, n, sq, sp, sred, so,
+                                 out + (size_t)b * d + h * 64, nullptr, st, 0, 0);
 }
 
 // cross-attention for one new token over F encoder frames: grid (n_heads, B)
@@ -401,12 +456,9 @@ __global__ void __launch_bounds__(kXThreads) cross_attn_kernel(const float* __re
   const bf16* kb = xkv + (size_t)b * F * fstride + h * 64;
   const bf16* vb = kb + d;
   const int slot = align_map_layer[h];
-  const int s_row = st->pos - n_prompt;
-  float* prob_dst = nullptr;
-  if (slot >= 0 && s_row >= 0 && s_row < T_cap && align_out != nullptr)
-    prob_dst = align_out + (((size_t)b * H_a + slot) * T_cap + s_row) * F;
-  attend_rows<kXThreads, 8, kFMax>(q + (size_t)b * d + h * 64, kb, vb, fstride, F, sq, sp, sred, so,
-                                   out + (size_t)b * d + h * 64, prob_dst);
+  float* prob_rows = (slot >= 0 && align_out != nullptr) ? align_out + ((size_t)b * H_a + slot) * T_cap * F : nullptr;
+  attend_rows<kXThreads, 8, kFMax, true>(q + (size_t)b * d + h * 64, kb, vb, fstride, F, sq, sp, sred, so,
+                                         out + (size_t)b * d + h * 64, prob_rows, st, n_prompt, T_cap);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -447,6 +499,8 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   __shared__ float sh[32];
   __shared__ int sh_i[32];
   __shared__ float sh_v[32];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   const int pos = p.st->pos;
   const int step = pos - (p.n_prompt - 1);   // index of the token this step generates
@@ -566,7 +620,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   }
 }
 
-__global__ void advance_kernel(DecState* st) { st->pos += 1; }
+__global__ void advance_kernel(DecState* st) {
+  pdl_trigger();
+  pdl_wait();
+  st->pos += 1;
+}
 
 // CW_DEC_PROFILE: keeps the GPU busy while the host queues the profiled launches, so that the event timestamps
 // bracket kernels that run back to back instead of host launch latency.
@@ -664,7 +722,7 @@ static int launch_gemv(cw_ctx* ctx, int epi, const GemvParams& p, cudaStream_t s
 #define CW_GEMV_LAUNCH(E)                                                                                         \
   {                                                                                                               \
     CW_CUDA(cudaFuncSetAttribute(gemv_kernel<NT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    gemv_kernel<NT, E><<<grid, block, smem, st>>>(p);                                                             \
+    CW_CUDA(launch_k(gemv_kernel<NT, E>, grid, block, smem, st, p));                                              \
   }
   switch (epi) {
     case EPI_QKV: CW_GEMV_LAUNCH(EPI_QKV) break;
@@ -690,8 +748,8 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   const int d = m.d_model, F = m.n_audio_ctx;
   const void** W = ctx->w;
   int rc;
-  embed_kernel<<<B, 256, 0, st>>>((const bf16*)W[CW_W_TOK_EMB], (const float*)W[CW_W_DEC_POS], bf.seq, m.n_text_ctx, bf.st,
-                                  bf.x, d);
+  CW_CUDA(launch_k(embed_kernel, dim3(B), dim3(256), 0, st, (const bf16*)W[CW_W_TOK_EMB], (const float*)W[CW_W_DEC_POS],
+                   (const int*)bf.seq, m.n_text_ctx, (const DecState*)bf.st, bf.x, d));
   CW_CHECK_LAUNCH("embed_kernel");
   ctx->launches += 1;
   CW_PROF(3);
@@ -707,8 +765,9 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
     g.out_f32 = bf.qbuf; g.kcache = bf.kc + l * cache_l; g.vcache = bf.vc + l * cache_l; g.d = d; g.n_ctx = m.n_text_ctx;
     g.st = bf.st;
     if ((rc = gemv(ctx, B, EPI_QKV, g, st)) != CW_OK) return rc;
-    self_attn_kernel<<<dim3(m.n_heads, B), kSThreads, 0, st>>>(bf.qbuf, bf.kc + l * cache_l, bf.vc + l * cache_l, bf.attn, bf.st,
-                                                          d, m.n_text_ctx);
+    CW_CUDA(launch_k(self_attn_kernel, dim3(m.n_heads, B), dim3(kSThreads), 0, st, (const float*)bf.qbuf,
+                     (const bf16*)(bf.kc + l * cache_l), (const bf16*)(bf.vc + l * cache_l), bf.attn, (const DecState*)bf.st, d,
+                     m.n_text_ctx));
     CW_CHECK_LAUNCH("self_attn_kernel");
     ctx->launches += 1;
     CW_PROF(1);
@@ -722,9 +781,9 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
     g.x_f32 = bf.x; g.ln_g = (const float*)L[CW_DL_LN2_G]; g.ln_b = (const float*)L[CW_DL_LN2_B];
     g.out_f32 = bf.qbuf; g.st = bf.st;
     if ((rc = gemv(ctx, B, EPI_F32, g, st)) != CW_OK) return rc;
-    cross_attn_kernel<<<dim3(m.n_heads, B), kXThreads, 0, st>>>(bf.qbuf, xkv + l * xkv_l, bf.attn, bf.st,
-                                                                 ctx->d_align_map + (size_t)l * m.n_heads, align_out,
-                                                                 m.n_align_heads, max_new, n_prompt, d, F);
+    CW_CUDA(launch_k(cross_attn_kernel, dim3(m.n_heads, B), dim3(kXThreads), 0, st, (const float*)bf.qbuf,
+                     (const bf16*)(xkv + l * xkv_l), bf.attn, (const DecState*)bf.st,
+                     (const int*)(ctx->d_align_map + (size_t)l * m.n_heads), align_out, m.n_align_heads, max_new, n_prompt, d, F));
     CW_CHECK_LAUNCH("cross_attn_kernel");
     ctx->launches += 1;
     CW_PROF(2);
@@ -743,7 +802,8 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
     g.x_bf16 = bf.hbuf; g.out_f32 = bf.x; g.st = bf.st;
     if ((rc = gemv(ctx, B, EPI_RESID, g, st)) != CW_OK) return rc;
   }
-  ln_rows_kernel<<<B, 256, 0, st>>>(bf.x, (const float*)W[CW_W_DEC_LNF_G], (const float*)W[CW_W_DEC_LNF_B], bf.xn, d);
+  CW_CUDA(launch_k(ln_rows_kernel, dim3(B), dim3(256), 0, st, (const float*)bf.x, (const float*)W[CW_W_DEC_LNF_G],
+                   (const float*)W[CW_W_DEC_LNF_B], bf.xn, d));
   CW_CHECK_LAUNCH("ln_rows_kernel");
   ctx->launches += 1;
   CW_PROF(3);
@@ -757,9 +817,9 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
   sp.max_new = max_new; sp.eos = m.eos_id; sp.no_ts = m.no_timestamps_id; sp.max_initial_ts = m.max_initial_timestamp_index;
   sp.flags = flags; sp.forced = forced; sp.logits_out = logits_out; sp.argmax_out = argmax_out;
-  sample_kernel<<<B, 1024, 0, st>>>(sp);
+  CW_CUDA(launch_k(sample_kernel, dim3(B), dim3(1024), 0, st, sp));
   CW_CHECK_LAUNCH("sample_kernel");
-  advance_kernel<<<1, 1, 0, st>>>(bf.st);
+  CW_CUDA(launch_k(advance_kernel, dim3(1), dim3(1), 0, st, bf.st));
   CW_CHECK_LAUNCH("advance_kernel");
   ctx->launches += 2;
   CW_PROF(3);
@@ -814,6 +874,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
 
   const int total_steps = n_prompt - 1 + max_new;  // positions 0 .. n_prompt+max_new-2
   // stream capture is not available on the legacy / per-thread default streams
+  g_use_pdl = !(flags & CW_DEC_NO_PDL);
   const bool profile = (flags & CW_DEC_PROFILE) != 0;
   StepProf prof;
   prof.on = profile; prof.st = st;
