@@ -51,7 +51,7 @@ class AutomaticSpeechRecognitionPipeline:
     def __init__(self, model, tokenizer=None, feature_extractor=None, chunk_length_s: float = 0, stride_length_s=None,
                  batch_size: int = 1, return_timestamps=None, torch_dtype=None, dtype=None, device=None,
                  generate_kwargs: Optional[Dict] = None, hf_batch_compat: bool = True, **_ignored):
-        if isinstance(model, Engine):
+        if isinstance(model, Engine) or (hasattr(model, "desc") and hasattr(model, "decode") and hasattr(model, "align")):
             self.engine = model
         else:
             dev = device if device is not None else 0
@@ -121,7 +121,7 @@ class AutomaticSpeechRecognitionPipeline:
         outputs: List[List[Dict]] = [[] for _ in waves]
         for b0 in range(0, len(plan), batch_size):
             items = plan[b0:b0 + batch_size]
-            host = torch.zeros(len(items), A.N_SAMPLES, dtype=torch.float32, pin_memory=True)
+            host = torch.zeros(len(items), A.N_SAMPLES, dtype=torch.float32, pin_memory=(eng.device.type == "cuda"))
             n_valid = []
             for k, (wi, start, length, _, _, _, _) in enumerate(items):
                 n = min(length, A.N_SAMPLES)

@@ -133,7 +133,10 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
     eos = cfg["eos_id"]
     max_new = _max_new(cfg, opts, n_prompt)
     seek = np.zeros(B, np.int64)
-    max_frames = np.asarray(num_frames, np.int64).copy()
+    # short-form input (<= 3000 frames): HF seeks over the whole padded window whatever the attention mask says
+    # (_retrieve_max_frames_and_seek, generation_whisper.py:1760-1772); `num_frames` only crops the alignment
+    max_frames = np.full(B, NUM_SEGMENT_FRAMES, np.int64)
+    num_frames = np.asarray(num_frames, np.int64)
     current_segments: List[List[Dict]] = [[] for _ in range(B)]
     flags = L.CW_DEC_SUPPRESS_EOS if opts.suppress_eos else 0
     if not opts.return_timestamps:
@@ -170,12 +173,16 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
             # alignment rows = G - 1: the last generated token is never fed back (generation_whisper.py:371-376)
             T_rows = np.full(nb, G_g - 1) if opts.hf_batch_compat else gen_counts - 1
             idx = np.asarray(active[sl])
-            F_len = (max_frames[idx] - seek[idx]) // 2
+            # weights[..., : (num_frames - seek) // 2] with Python slice semantics (generation_whisper.py:1147-1150,354):
+            # a negative bound counts from the end, 0 leaves no frame (-> every jump index is -1)
+            k = (num_frames[idx] - seek[idx]) // 2
+            F_len = np.where(k >= 0, np.minimum(k, cfg["n_audio_ctx"]), np.maximum(cfg["n_audio_ctx"] + k, 0))
             if out["align"] is not None and T_rows.max() > 0:
                 j = engine.align(out["align"], torch.from_numpy(T_rows.astype(np.int32)),
                                  torch.from_numpy(np.maximum(F_len, 1).astype(np.int32)), cfg["median_filter_width"])
                 engine.sync()
-                jump_g = j.cpu().numpy()
+                jump_g = j.cpu().numpy().copy()
+                jump_g[F_len == 0] = -1
                 if stats is not None:
                     stats["d2h_bytes"] = stats.get("d2h_bytes", 0) + jump_g.nbytes
             else:

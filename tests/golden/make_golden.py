@@ -163,29 +163,63 @@ def gen_pauses():
     print("pauses_ref.json", len(out))
 
 
+def _oracle_pipeline(m, tok, n_mels, batch_size):
+    """The product's host logic driven by the CPU oracle engine (tests/oracle_engine.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_engine import OracleEngine
+    from crisperwhisper_b200 import weights as Wt
+    from crisperwhisper_b200.asr_pipeline import AutomaticSpeechRecognitionPipeline
+    from transformers import WhisperFeatureExtractor
+    cfg = Wt.config_from_hf(m)
+    cfg["lang_id"], cfg["task_id"] = H.TOK_IDS["en"], H.TOK_IDS["transcribe"]
+    eng = OracleEngine({k: v.float() for k, v in m.state_dict().items()}, cfg)
+    eng.desc = cfg
+    pipe = AutomaticSpeechRecognitionPipeline(eng, tokenizer=tok, feature_extractor=WhisperFeatureExtractor(feature_size=n_mels),
+                                              chunk_length_s=30, batch_size=batch_size, return_timestamps="word")
+    return pipe, eng
+
+
 def gen_pipeline():
     """cfg 1 / cfg 3 plumbing goldens: tiny random model + synthetic tokenizer through the reference's exact pipeline
-    call, then REF/utils.py."""
+    call, then REF/utils.py.  Seeds are searched so that the greedy path has no near-tie (top-1/top-2 score margin
+    > 0.35 at every step, measured with the fp32 oracle): those cases are also valid for the bf16 GPU kernels."""
     sys.path.insert(0, "/root/reference")
     import utils as ref_utils
+    import warnings
     tok = H.synthetic_tokenizer()
     out = {}
     long70 = np.concatenate([H.speechlike(3), H.noise(4), H.noise(5, 160000)])
-    for name, n_mels, seed, wave, bs, max_new in (
-            ("clip5s", 128, 0, H.noise(0, 80000), 16, 40),
-            ("clip70s", 128, 1, long70, 16, 24),
-            ("clip70s_bs1", 128, 1, long70, 1, 24),
-            ("clip12s_80", 80, 2, H.speechlike(6, 12 * 16000), 2, 30)):
+    for name, n_mels, wave, bs, max_new in (
+            ("clip5s", 128, H.noise(0, 80000), 16, 16),
+            ("clip70s", 128, long70, 16, 24),
+            ("clip70s_bs1", 128, long70, 1, 24),
+            ("clip12s_80", 80, H.speechlike(6, 12 * 16000), 2, 30)):
+        best = None
+        for seed in range(120):
+            m = H.build_model(H.tiny_hf_config(n_mels=n_mels), seed=seed, logit_scale=8.0, pos_scale=20.0)
+            opipe, eng = _oracle_pipeline(m, tok, n_mels, bs)
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    mine = opipe(wave.copy(), generate_kwargs={"max_new_tokens": max_new})
+            except IndexError:  # HF's _split_tokens_on_unicode trips over some invalid UTF-8 byte runs of a random model
+                continue
+            if len(mine["chunks"]) >= 2 and (best is None or eng.min_margin > best[1]):
+                best = (seed, eng.min_margin, mine)
+            if best is not None and best[1] > 0.35:
+                break
+        assert best is not None, name
+        seed, margin, mine = best
         m = H.build_model(H.tiny_hf_config(n_mels=n_mels), seed=seed, logit_scale=8.0, pos_scale=20.0)
         pipe = H.build_pipeline(m, tok, batch_size=bs)
-        import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             res = pipe(wave.copy(), generate_kwargs={"max_new_tokens": max_new})
+        assert res["text"] == mine["text"], (name, seed)
         adj = ref_utils.adjust_pauses_for_hf_pipeline_output(copy.deepcopy(res))
         out[name] = {"n_mels": n_mels, "seed": seed, "batch_size": bs, "max_new_tokens": max_new, "logit_scale": 8.0,
-                     "pos_scale": 20.0, "pipeline": res, "adjusted": adj}
-        print(name, len(res["chunks"]), repr(res["text"][:60]))
+                     "pos_scale": 20.0, "min_margin": margin, "pipeline": res, "adjusted": adj}
+        print(name, "seed", seed, "margin %.3f" % margin, len(res["chunks"]), repr(res["text"][:50]))
     with open(os.path.join(HERE, "pipeline_hf.json"), "w") as f:
         json.dump(out, f, indent=1)
 
