@@ -173,10 +173,15 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
             # alignment rows = G - 1: the last generated token is never fed back (generation_whisper.py:371-376)
             T_rows = np.full(nb, G_g - 1) if opts.hf_batch_compat else gen_counts - 1
             idx = np.asarray(active[sl])
-            # weights[..., : (num_frames - seek) // 2] with Python slice semantics (generation_whisper.py:1147-1150,354):
-            # a negative bound counts from the end, 0 leaves no frame (-> every jump index is -1)
+            # weights[..., : (num_frames - seek) // 2] with Python slice semantics (generation_whisper.py:1147-1150):
+            # a negative bound counts from the end and 0 leaves no frame (-> every jump index is -1).
+            # When the bound is the same for the whole batch HF slices twice (:315-329 and again :354).
             k = (num_frames[idx] - seek[idx]) // 2
-            F_len = np.where(k >= 0, np.minimum(k, cfg["n_audio_ctx"]), np.maximum(cfg["n_audio_ctx"] + k, 0))
+            F_full = cfg["n_audio_ctx"]
+            crop = lambda width, kk: np.where(kk >= 0, np.minimum(kk, width), np.maximum(width + kk, 0))
+            F_len = crop(np.full(nb, F_full), k)
+            if len(np.unique(k)) == 1:
+                F_len = crop(F_len, k)
             if out["align"] is not None and T_rows.max() > 0:
                 j = engine.align(out["align"], torch.from_numpy(T_rows.astype(np.int32)),
                                  torch.from_numpy(np.maximum(F_len, 1).astype(np.int32)), cfg["median_filter_width"])
