@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kSThreads) self_attn_kernel(const float* __res
 static constexpr int kXThreads = 512;
 static constexpr int kFMax = 1500;
 
-__global__ void __launch_bounds__(kXThreads) cross_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ xkv,
+__global__ void __launch_bounds__(kXThreads, 2) cross_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ xkv,
                                                               bf16* __restrict__ out, const DecState* st,
                                                               const int* __restrict__ align_map_layer, float* align_out,
                                                               int H_a, int T_cap, int n_prompt, int d, int F) {
