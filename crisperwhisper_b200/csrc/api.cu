@@ -79,6 +79,7 @@ void cw_destroy(cw_ctx* ctx) {
   decode_state_free(ctx);
   if (ctx->d_align_map) cudaFree(ctx->d_align_map);
   if (ctx->d_suppress) cudaFree(ctx->d_suppress);
+  if (ctx->d_w) cudaFree((void*)ctx->d_w);
   free((void*)ctx->w);
   free(ctx);
 }
@@ -106,6 +107,9 @@ int cw_load_weights(cw_ctx* ctx, const void* const* dev_ptrs, int n_ptrs, const 
   ctx->w = (const void**)malloc(sizeof(void*) * n_ptrs);
   memcpy((void*)ctx->w, dev_ptrs, sizeof(void*) * n_ptrs);
   ctx->n_w = n_ptrs;
+  if (ctx->d_w) cudaFree((void*)ctx->d_w);
+  CW_CUDA(cudaMalloc((void**)&ctx->d_w, sizeof(void*) * n_ptrs));
+  CW_CUDA(cudaMemcpy((void*)ctx->d_w, dev_ptrs, sizeof(void*) * n_ptrs, cudaMemcpyHostToDevice));
   ModelDesc& m = ctx->md;
   m.d_model = d->d_model; m.n_heads = d->n_heads; m.enc_layers = d->enc_layers; m.dec_layers = d->dec_layers;
   m.ffn_dim = d->ffn_dim; m.vocab = d->vocab; m.vocab_padded = d->vocab_padded; m.n_mels = d->n_mels;

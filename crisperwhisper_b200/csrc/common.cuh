@@ -63,6 +63,7 @@ struct cw_ctx {
   bool has_weights;
   cw::ModelDesc md;
   const void** w;        // host copy of the weight pointer table
+  const void** d_w;      // device copy (decode megakernel)
   int n_w;
   // device-side config blobs (allocated once at load time)
   int32_t* d_align_map;  // [dec_layers * n_heads] -> alignment slot or -1

@@ -495,14 +495,9 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
-  __shared__ float sh[32];
-  __shared__ int sh_i[32];
-  __shared__ float sh_v[32];
-  pdl_trigger();
-  pdl_wait();
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int pos = p.st->pos;
+__device__ __forceinline__ void sample_body(const SampleParams& p, const int b, const int pos, float* sh, int* sh_i,
+                                            float* sh_v) {
+  const int tid = threadIdx.x;
   const int step = pos - (p.n_prompt - 1);   // index of the token this step generates
   if (step < 0 || step >= p.max_new) return; // prompt prefill: nothing to sample
   float* lg = p.logits + (size_t)b * p.Vp;
@@ -620,6 +615,17 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   }
 }
 
+__global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
+  __shared__ float sh[32];
+  __shared__ int sh_i[32];
+  __shared__ float sh_v[32];
+  pdl_trigger();
+  pdl_wait();
+  sample_body(p, blockIdx.x, p.st->pos, sh, sh_i, sh_v);
+}
+
+#include "decoder_mega.cuh"
+
 __global__ void advance_kernel(DecState* st) {
   pdl_trigger();
   pdl_wait();
@@ -657,6 +663,7 @@ void decode_state_free(cw_ctx* ctx) {
 struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
+  float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar;
 };
 
 static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
@@ -676,6 +683,10 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.st = (DecState*)take(sizeof(DecState));
   t.finished = (int*)take((size_t)B * 4);
   t.seq = (int*)take((size_t)B * m.n_text_ctx * 4);
+  t.xpart = (float*)take((size_t)B * m.n_heads * kXSplit * 66 * 4);
+  t.xscore = (float*)take((size_t)B * m.n_heads * m.n_audio_ctx * 4);
+  t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
+  t.bar = (unsigned int*)take(256);
   if (o) *o = t;
   return a.off + 256;
 }
@@ -826,10 +837,45 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   return CW_OK;
 }
 
+// one cooperative launch for the whole step
+static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
+                             const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
+  const ModelDesc& m = ctx->md;
+  MegaParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = (const void* const*)ctx->d_w;
+  p.enc_layers = m.enc_layers; p.dec_layers = m.dec_layers; p.d = m.d_model; p.n_heads = m.n_heads; p.ffn = m.ffn_dim;
+  p.Vp = m.vocab_padded; p.n_ctx = m.n_text_ctx; p.F = m.n_audio_ctx; p.B = B;
+  p.x = bf.x; p.qbuf = bf.qbuf; p.attn = bf.attn; p.hbuf = bf.hbuf; p.logits = bf.logits; p.kc = bf.kc; p.vc = bf.vc;
+  p.st = bf.st; p.seq = bf.seq; p.xkv = xkv; p.align_map = ctx->d_align_map; p.align_out = align_out;
+  p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
+  p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.bar = bf.bar;
+  SampleParams& sp = p.sp;
+  sp.logits = bf.logits; sp.suppress = ctx->d_suppress; sp.seq = bf.seq; sp.seq_ld = m.n_text_ctx;
+  sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
+  sp.max_new = max_new; sp.eos = m.eos_id; sp.no_ts = m.no_timestamps_id; sp.max_initial_ts = m.max_initial_timestamp_index;
+  sp.flags = flags; sp.forced = forced; sp.logits_out = logits_out; sp.argmax_out = argmax_out;
+  const int kmax = m.ffn_dim > m.d_model ? m.ffn_dim : m.d_model;
+  const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4;
+  CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
+  CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctx->sm_count); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CW_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel, p));
+  ctx->launches += 1;
+  return CW_OK;
+}
+
 __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
-                                int eos) {
+                                int eos, unsigned int* xcount, int n_xcount, unsigned int* bar) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { st->pos = 0; st->n_finished = 0; }
+  if (i == 0) { st->pos = 0; st->n_finished = 0; *bar = 0u; }
+  if (i < n_xcount) xcount[i] = 0u;
   if (i < B) finished[i] = 0;
   if (i < B * seq_ld) {
     int b = i / seq_ld, t = i - b * seq_ld;
@@ -868,7 +914,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
 
   int n_init = B * m.n_text_ctx;
   dec_init_kernel<<<(n_init + 255) / 256, 256, 0, st>>>(bf.st, bf.finished, bf.seq, m.n_text_ctx, prompt, n_prompt, B,
-                                                        m.eos_id);
+                                                        m.eos_id, bf.xcount, B * m.n_heads, bf.bar);
   CW_CHECK_LAUNCH("dec_init_kernel");
   ctx->launches += 1;
 
@@ -876,6 +922,12 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   // stream capture is not available on the legacy / per-thread default streams
   g_use_pdl = !(flags & CW_DEC_NO_PDL);
   const bool profile = (flags & CW_DEC_PROFILE) != 0;
+  // B <= 8: the whole step is one persistent cooperative kernel; otherwise (or on request) one kernel per operator
+  const bool use_mega = (B <= 8) && (m.d_model <= 1280) && !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
+  auto step_fn = [&](cw_ctx* c) -> int {
+    if (use_mega) return enqueue_step_mega(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+    return enqueue_step(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+  };
   StepProf prof;
   prof.on = profile; prof.st = st;
   if (profile) { for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; } }
@@ -894,7 +946,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       cudaGraph_t graph;
       long long launches_before = ctx->launches;
       CW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+      rc = step_fn(ctx);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       ctx->launches = launches_before;  // capture does not execute anything
       if (rc != CW_OK) { if (ce == cudaSuccess && graph) cudaGraphDestroy(graph); return rc; }
@@ -907,7 +959,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       G->forced = forced; G->align_out = align_out; G->logits_out = logits_out; G->argmax_out = argmax_out;
     }
   }
-  const long long per_step = 5 + 8LL * m.dec_layers;  // kernels in one step
+  const long long per_step = use_mega ? 1 : 5 + 8LL * m.dec_layers;  // kernels in one step
   int steps_done = 0;  // generated tokens
   int h_state[4] = {0, 0, 0, 0};
   if (profile) {
@@ -922,7 +974,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       ctx->launches += per_step;
     } else {
       if (profile) { g_prof = &prof; prof.mark(3); }
-      rc = enqueue_step(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+      rc = step_fn(ctx);
       g_prof = nullptr;
       if (rc != CW_OK) return rc;
     }

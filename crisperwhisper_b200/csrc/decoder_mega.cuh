@@ -1,0 +1,479 @@
+// decoder_mega.cuh — one persistent cooperative kernel per decode step (included by decoder.cu).
+//
+// The multi-kernel step (decoder.cu) is latency-bound at small batch: 262 short dependent kernels per token.
+// Here the whole step — embed, 32 x {LN+qkv, self-attention, o-proj, LN+q_c, cross-attention, o_c-proj, LN+fc1+GELU, fc2},
+// final LN + logits, logits processors + argmax — runs in ONE launch of #SM CTAs x 512 threads that stay resident and
+// meet at grid-wide barriers (monotonic counter in global memory, bounded spin).  Work distribution per phase:
+//   projections   16-row tiles of the weight matrix; KW warps split K for one tile (mma.sync.m16n8k16, weights
+//                 streamed HBM -> A fragments exactly once), 16/KW tiles in flight per CTA, named barriers per group
+//   self-attn     one 8-warp group per (sample, head)
+//   cross-attn    (sample, head) split 3-way over the 1500 frames -> 480 four-warp groups <= 592 slots: one wave;
+//                 the group that arrives last at the per-(sample, head) counter merges the three partial softmaxes,
+//                 writes the head output and, for alignment heads, the normalised probabilities
+// Activations cross SMs between phases, so they are read with ld.global.cg (L2) — L1 is not coherent.
+// Supports B <= 8 (one n8 MMA tile); larger batches use the multi-kernel path.
+#pragma once
+// (included inside namespace cw by decoder.cu)
+
+static constexpr int kMegaThreads = 512;
+static constexpr int kMegaWarps = 16;
+static constexpr int kXSplit = 3;          // cross-attention frame splits per (sample, head)
+static constexpr int kXFrames = 500;       // frames per split (1500 / 3)
+
+struct MegaParams {
+  const void* const* W;      // device copy of the weight pointer table
+  int enc_layers, dec_layers, d, n_heads, ffn, Vp, n_ctx, F, B;
+  // activations / state
+  float* x; float* qbuf; bf16* attn; bf16* hbuf; float* logits;
+  bf16* kc; bf16* vc;
+  DecState* st;
+  const int* seq;
+  const bf16* xkv;
+  const int* align_map;      // [dec_layers * n_heads]
+  float* align_out; int H_a, T_cap, n_prompt;
+  // cross-attention merge scratch
+  float* xpart;              // [B*H][kXSplit][66]  (m, l, o[64])
+  float* xscore;             // [B*H][F] exp(score - m_split)
+  unsigned int* xcount;      // [B*H]
+  unsigned int* bar;         // grid barrier counter
+  SampleParams sp;
+};
+
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ld_cg4(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_cg16(const uint4* p) { return __ldcg(p); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel). Bounded spin -> trap.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(bar, 1u);
+    const unsigned int target = (old / nblocks + 1u) * nblocks;
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (++spins > (1u << 26)) { printf("libcrisper decode: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---- activation staging: rows of B samples -> bf16 [8][K+32] in smem --------------------------------------
+__device__ __noinline__ void stage_ln(bf16* xs, int XS, const float* x, const float* g, const float* bt, int K, int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = K >> 7;
+  if (warp < 8) {
+    bf16* dst = xs + (size_t)warp * XS;
+    if (warp < B) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * K);
+      float4 v[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) v[i] = (i < nv) ? ld_cg4(xr + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)K;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        if (i < nv) {
+          float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+          q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q / (float)K + 1e-5f);
+      const float4* g4 = reinterpret_cast<const float4*>(g);
+      const float4* b4 = reinterpret_cast<const float4*>(bt);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        if (i < nv) {
+          const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(dst + 4 * (lane + 32 * i)) = u;
+        }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) dst[k] = __float2bfloat16(0.f);
+    }
+  }
+}
+
+__device__ __noinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
+  const int vec_per_row = K >> 3;
+  const int total = 8 * vec_per_row;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kMegaThreads) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kMegaThreads;
+      v[u] = make_uint4(0, 0, 0, 0);
+      if (i < total) {
+        const int b = i / vec_per_row, c = i - b * vec_per_row;
+        if (b < B) v[u] = ld_cg16(reinterpret_cast<const uint4*>(src + (size_t)b * K + c * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kMegaThreads;
+      if (i < total) {
+        const int b = i / vec_per_row, c = i - b * vec_per_row;
+        *reinterpret_cast<uint4*>(xs + (size_t)b * XS + c * 8) = v[u];
+      }
+    }
+  }
+}
+
+// pick the widest K-split (<= kMax warps per tile) whose slice is a multiple of 32
+#define CW_MEGA_GEMV(kMax, EPI, Wp, bias, N, K, XS)                                                          \
+  do {                                                                                                       \
+    if ((kMax) >= 16 && (K) % 512 == 0) mega_gemv<16, EPI>(Wp, bias, N, K, B, xs, XS, red, o);               \
+    else if ((kMax) >= 8 && (K) % 256 == 0) mega_gemv<8, EPI>(Wp, bias, N, K, B, xs, XS, red, o);            \
+    else mega_gemv<4, EPI>(Wp, bias, N, K, B, xs, XS, red, o);                                               \
+  } while (0)
+
+struct GemvOut {
+  float* out_f32;   // F32 / RESID / QKV(q)
+  bf16* out_bf16;   // GELU_BF16
+  bf16* kcache; bf16* vcache;
+  int d, n_ctx, pos;
+};
+
+// Projection phase: all 16-row tiles of W [N, K]; KW warps per tile, 16/KW tiles in flight per CTA.
+// Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
+template <int KW, int EPI>
+__device__ __noinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
+                                          const bf16* xs, int XS, float* red, const GemvOut& o) {
+  constexpr int S = kMegaWarps / KW;      // concurrent tiles per CTA
+  constexpr int GT = KW * 32;             // threads per group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / KW, wl = warp - grp * KW;
+  const int gtid = threadIdx.x - grp * GT;
+  const int g = lane >> 2, t = lane & 3;
+  const int n_tiles = N >> 4;
+  const int kslice = K / KW;
+  const int kbeg = wl * kslice;
+  const int chunks = kslice >> 5;
+  float* myred = red + (size_t)warp * 128;
+  const float* gred = red + (size_t)grp * KW * 128;
+  const int stride = gridDim.x * S;
+  for (int tile = blockIdx.x + gridDim.x * grp; tile < n_tiles; tile += stride) {
+    const int n0 = tile << 4;
+    const bf16* w0 = W + (size_t)(n0 + g) * K + kbeg + 8 * t;
+    const bf16* w1 = w0 + (size_t)8 * K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int U = 5;
+    for (int c0 = 0; c0 < chunks; c0 += U) {
+      uint4 a0[U], a1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (c0 + u < chunks) {
+          a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+          a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (c0 + u < chunks) {
+          const int kk = kbeg + (c0 + u) * 32 + 8 * t;
+          const uint4 xb = *reinterpret_cast<const uint4*>(xs + (size_t)g * XS + kk);
+          mma16816(acc, a0[u].x, a1[u].x, a0[u].y, a1[u].y, xb.x, xb.y);
+          mma16816(acc, a0[u].z, a1[u].z, a0[u].w, a1[u].w, xb.z, xb.w);
+        }
+      }
+    }
+    myred[g * 8 + 2 * t] = acc[0];
+    myred[g * 8 + 2 * t + 1] = acc[1];
+    myred[(g + 8) * 8 + 2 * t] = acc[2];
+    myred[(g + 8) * 8 + 2 * t + 1] = acc[3];
+    named_bar(1 + grp, GT);
+    if (gtid < 128) {
+      const int r = gtid & 15, bcol = gtid >> 4;
+      if (bcol < B) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < KW; ++w) v += gred[w * 128 + r * 8 + bcol];
+        const int n = n0 + r;
+        if (bias) v += __ldg(bias + n);
+        if (EPI == EPI_F32) {
+          o.out_f32[(size_t)bcol * N + n] = v;
+        } else if (EPI == EPI_RESID) {
+          float* px = o.out_f32 + (size_t)bcol * N + n;
+          *px = ld_cg(px) + v;
+        } else if (EPI == EPI_GELU_BF16) {
+          o.out_bf16[(size_t)bcol * N + n] = __float2bfloat16(gelu_erf_d(v));
+        } else {
+          const int d = o.d;
+          if (n < d) o.out_f32[(size_t)bcol * d + n] = v;
+          else if (n < 2 * d) o.kcache[((size_t)bcol * o.n_ctx + o.pos) * d + (n - d)] = __float2bfloat16(v);
+          else o.vcache[((size_t)bcol * o.n_ctx + o.pos) * d + (n - 2 * d)] = __float2bfloat16(v);
+        }
+      }
+    }
+    named_bar(1 + grp, GT);  // red is reused by the next tile of this group
+  }
+}
+
+// Attention of one query row over n rows by a group of GT threads (8 threads per row). Returns, in smem/regs:
+// sp[j] = exp(score_j - m), local max m and sum l (broadcast to every thread), acc -> so then out[64] in so[0][..].
+template <int GT, int UN>
+__device__ __noinline__ void group_attend(const float* __restrict__ q64, const bf16* __restrict__ kb,
+                                             const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
+                                             float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/, float& m_out,
+                                             float& l_out) {
+  constexpr int G = GT / 8;
+  const int sub = gtid & 7, grp = gtid >> 3;
+  if (gtid < 64) sq[gtid] = ld_cg(q64 + gtid);
+  named_bar(bar_id, GT);
+  float qv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e];
+  for (int base = 0; base < n; base += G * UN) {
+    uint4 u[UN];
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = base + grp + G * x;
+      u[x] = make_uint4(0, 0, 0, 0);
+      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+    }
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = base + grp + G * x;
+      float s = (j < n) ? dot8(u[x], qv) : 0.f;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (sub == 0 && j < n) sp[j] = s;
+    }
+  }
+  named_bar(bar_id, GT);
+  float lmax = -INFINITY;
+  for (int j = gtid; j < n; j += GT) lmax = fmaxf(lmax, sp[j]);
+  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  if ((gtid & 31) == 0) sred[gtid >> 5] = lmax;
+  named_bar(bar_id, GT);
+  float mx = sred[0];
+#pragma unroll
+  for (int w = 1; w < GT / 32; ++w) mx = fmaxf(mx, sred[w]);
+  named_bar(bar_id, GT);
+  float lsum = 0.f;
+  for (int j = gtid; j < n; j += GT) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((gtid & 31) == 0) sred[gtid >> 5] = lsum;
+  named_bar(bar_id, GT);
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < GT / 32; ++w) tot += sred[w];
+  m_out = mx; l_out = tot;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int base = 0; base < n; base += G * UN) {
+    uint4 u[UN];
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = base + grp + G * x;
+      u[x] = make_uint4(0, 0, 0, 0);
+      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
+    }
+#pragma unroll
+    for (int x = 0; x < UN; ++x) {
+      const int j = base + grp + G * x;
+      if (j < n) {
+        const float pj = sp[j];
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[x]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(h2[e]);
+          acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+          acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) so[grp * 65 + sub * 8 + e] = acc[e];
+  named_bar(bar_id, GT);
+  if (gtid < 64) {
+    float v = 0.f;
+    for (int r = 0; r < G; ++r) v += so[r * 65 + gtid];
+    so[gtid] = v;  // row 0, column gtid (each thread only overwrites the element it just finished reading in its column)
+  }
+  named_bar(bar_id, GT);
+}
+
+__device__ __noinline__ void mega_sample(const SampleParams& sp, int b, int pos, float* sh, int* sh_i, float* sh_v) {
+  sample_body(sp, b, pos, sh, sh_i, sh_v);
+}
+
+// dynamic smem: xs bf16 [8][ffn+32] | red f32 [16][128] | attention scratch (aliases xs)
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams p) {
+  extern __shared__ __align__(16) unsigned char msm[];
+  __shared__ float sh[32];
+  __shared__ int sh_i[32];
+  __shared__ float sh_v[32];
+  __shared__ int s_flag[4];
+  const int d = p.d, B = p.B, H = p.n_heads, F = p.F;
+  const int XSd = d + 32, XSf = p.ffn + 32;
+  bf16* xs = reinterpret_cast<bf16*>(msm);
+  float* red = reinterpret_cast<float*>(msm + (size_t)8 * XSf * 2);
+  float* ascr = reinterpret_cast<float*>(msm);  // attention scratch aliases xs (phases never overlap inside a CTA)
+  const unsigned int G = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int pos = p.st->pos;  // written by the previous launch only
+
+  // ---- embed: x[b] = tok_emb[token] + pos_emb[pos] ---------------------------------------------------------
+  {
+    const bf16* emb = (const bf16*)p.W[CW_W_TOK_EMB];
+    const float* ptab = (const float*)p.W[CW_W_DEC_POS] + (size_t)pos * d;
+    for (int i = blockIdx.x * kMegaThreads + tid; i < B * d; i += G * kMegaThreads) {
+      const int b = i / d, k = i - b * d;
+      const int tok = p.seq[(size_t)b * p.n_ctx + pos];
+      p.x[i] = __bfloat162float(emb[(size_t)tok * d + k]) + ptab[k];
+    }
+  }
+  grid_barrier(p.bar, G);
+
+  const size_t cache_l = (size_t)B * p.n_ctx * d;
+  const size_t xkv_l = (size_t)B * F * 2 * d;
+  for (int l = 0; l < p.dec_layers; ++l) {
+    const void* const* L = p.W + CW_W_GLOBAL_COUNT + (size_t)p.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
+    bf16* kc = p.kc + l * cache_l;
+    bf16* vc = p.vc + l * cache_l;
+    GemvOut o;
+    // P1: q, k, v = Wqkv . LN1(x)
+    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN1_G], (const float*)L[CW_DL_LN1_B], d, B);
+    __syncthreads();
+    o.out_f32 = p.qbuf; o.out_bf16 = nullptr; o.kcache = kc; o.vcache = vc; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
+    CW_MEGA_GEMV(8, EPI_QKV, (const bf16*)L[CW_DL_WQKV], (const float*)L[CW_DL_BQKV], 3 * d, d, XSd);
+    grid_barrier(p.bar, G);
+    // P2: causal self-attention, one 8-warp group per (sample, head)
+    {
+      const int grp = warp >> 3, gtid = tid & 255;
+      const int task = blockIdx.x + G * grp;
+      float* base = ascr + grp * 4096;     // sq[64] | sp[448] | sred[8] | so[32*65]
+      if (task < B * H) {
+        const int b = task / H, h = task - b * H;
+        float m_, l_;
+        group_attend<256, 4>(p.qbuf + (size_t)b * d + h * 64, kc + (size_t)b * p.n_ctx * d + h * 64,
+                             vc + (size_t)b * p.n_ctx * d + h * 64, (size_t)d, pos + 1, gtid, 1 + grp, base, base + 64,
+                             base + 64 + 448, base + 64 + 448 + 8, m_, l_);
+        if (gtid < 64) p.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(base[64 + 448 + 8 + gtid] / l_);
+      }
+    }
+    grid_barrier(p.bar, G);
+    // P3: x += Wo . attn + bo
+    stage_bf16(xs, XSd, p.attn, d, B);
+    __syncthreads();
+    o.out_f32 = p.x;
+    CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WO], (const float*)L[CW_DL_BO], d, d, XSd);
+    grid_barrier(p.bar, G);
+    // P4: q_c = Wqc . LN2(x)
+    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN2_G], (const float*)L[CW_DL_LN2_B], d, B);
+    __syncthreads();
+    o.out_f32 = p.qbuf;
+    CW_MEGA_GEMV(8, EPI_F32, (const bf16*)L[CW_DL_WQC], (const float*)L[CW_DL_BQC], d, d, XSd);
+    grid_barrier(p.bar, G);
+    // P5: cross-attention, (sample, head) x 3 frame splits, 4-warp groups
+    {
+      const int grp = warp >> 2, gtid = tid & 127;
+      const int sub_id = blockIdx.x + G * grp;
+      float* base = ascr + grp * 2048;     // sq[64] | sp[500] | sred[4] | so[16*65]
+      if (sub_id < B * H * kXSplit) {
+        const int task = sub_id / kXSplit, split = sub_id - task * kXSplit;
+        const int b = task / H, h = task - b * H;
+        const int f0 = split * kXFrames;
+        const int nf = min(kXFrames, F - f0);
+        const size_t fstride = (size_t)2 * d;
+        const bf16* kb = p.xkv + l * xkv_l + ((size_t)b * F + f0) * fstride + h * 64;
+        float m_, l_;
+        float* sp = base + 64;
+        float* so = base + 64 + 500 + 4;
+        group_attend<128, 8>(p.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base, sp, base + 64 + 500,
+                             so, m_, l_);
+        const int slot = p.align_map[l * H + h];
+        float* part = p.xpart + ((size_t)task * kXSplit + split) * 66;
+        if (gtid < 64) part[2 + gtid] = so[gtid];
+        if (gtid == 0) { part[0] = m_; part[1] = l_; }
+        if (slot >= 0) {
+          float* sc = p.xscore + (size_t)task * F + f0;
+          for (int j = gtid; j < nf; j += 128) sc[j] = sp[j];
+        }
+        __threadfence();
+        named_bar(1 + grp, 128);
+        if (gtid == 0) {
+          const unsigned int old = atomicAdd(p.xcount + task, 1u);
+          s_flag[grp] = (old == kXSplit - 1) ? 1 : 0;
+          if (old == kXSplit - 1) p.xcount[task] = 0;
+        }
+        named_bar(1 + grp, 128);
+        if (s_flag[grp]) {  // last arriver: merge the partial softmaxes
+          __threadfence();
+          const float* pt = p.xpart + (size_t)task * kXSplit * 66;
+          float mi[kXSplit], li[kXSplit];
+          float M = -INFINITY;
+#pragma unroll
+          for (int s = 0; s < kXSplit; ++s) { mi[s] = ld_cg(pt + s * 66); li[s] = ld_cg(pt + s * 66 + 1); M = fmaxf(M, mi[s]); }
+          float Lsum = 0.f, wi[kXSplit];
+#pragma unroll
+          for (int s = 0; s < kXSplit; ++s) { wi[s] = expf(mi[s] - M); Lsum += li[s] * wi[s]; }
+          const float inv = 1.f / Lsum;
+          if (gtid < 64) {
+            float v = 0.f;
+#pragma unroll
+            for (int s = 0; s < kXSplit; ++s) v += ld_cg(pt + s * 66 + 2 + gtid) * wi[s];
+            p.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(v * inv);
+          }
+          const int s_row = pos - p.n_prompt;
+          if (slot >= 0 && p.align_out != nullptr && s_row >= 0 && s_row < p.T_cap) {
+            float* dst = p.align_out + (((size_t)b * p.H_a + slot) * p.T_cap + s_row) * F;
+            const float* sc = p.xscore + (size_t)task * F;
+            for (int j = gtid; j < F; j += 128) dst[j] = ld_cg(sc + j) * wi[j / kXFrames] * inv;
+          }
+        }
+      }
+    }
+    grid_barrier(p.bar, G);
+    // P6: x += Woc . attn + boc
+    stage_bf16(xs, XSd, p.attn, d, B);
+    __syncthreads();
+    o.out_f32 = p.x;
+    CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WOC], (const float*)L[CW_DL_BOC], d, d, XSd);
+    grid_barrier(p.bar, G);
+    // P7: h = GELU(W1 . LN3(x) + b1)
+    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN3_G], (const float*)L[CW_DL_LN3_B], d, B);
+    __syncthreads();
+    o.out_bf16 = p.hbuf;
+    CW_MEGA_GEMV(4, EPI_GELU_BF16, (const bf16*)L[CW_DL_W1], (const float*)L[CW_DL_B1], p.ffn, d, XSd);
+    grid_barrier(p.bar, G);
+    // P8: x += W2 . h + b2
+    stage_bf16(xs, XSf, p.hbuf, p.ffn, B);
+    __syncthreads();
+    o.out_f32 = p.x;
+    CW_MEGA_GEMV(16, EPI_RESID, (const bf16*)L[CW_DL_W2], (const float*)L[CW_DL_B2], d, p.ffn, XSf);
+    grid_barrier(p.bar, G);
+  }
+  // ---- final LayerNorm + tied proj_out --------------------------------------------------------------------
+  {
+    stage_ln(xs, XSd, p.x, (const float*)p.W[CW_W_DEC_LNF_G], (const float*)p.W[CW_W_DEC_LNF_B], d, B);
+    __syncthreads();
+    GemvOut o;
+    o.out_f32 = p.logits; o.out_bf16 = nullptr; o.kcache = nullptr; o.vcache = nullptr; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
+    CW_MEGA_GEMV(4, EPI_F32, (const bf16*)p.W[CW_W_TOK_EMB], (const float*)nullptr, p.Vp, d, XSd);
+  }
+  grid_barrier(p.bar, G);
+  if ((int)blockIdx.x < B) mega_sample(p.sp, blockIdx.x, pos, sh, sh_i, sh_v);
+  // the position advances once every CTA has read `pos` (all did, at kernel entry, before the first barrier)
+  if (blockIdx.x == 0 && tid == 0) p.st->pos = pos + 1;
+}
+

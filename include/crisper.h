@@ -186,6 +186,7 @@ int cw_encode(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xkv
 #define CW_DEC_SUPPRESS_EOS 1     /* never pick eos (fixed-length benchmark decode) */
 #define CW_DEC_NO_TIMESTAMP_RULES 2 /* skip WhisperTimeStampLogitsProcessor (return_timestamps=False) */
 #define CW_DEC_NO_GRAPH 4         /* launch kernels directly instead of replaying a captured CUDA graph */
+#define CW_DEC_NO_MEGA 32         /* one kernel per operator instead of the persistent cooperative step kernel (B <= 8) */
 #define CW_DEC_NO_PDL 16          /* plain stream-ordered launches instead of programmatic dependent launch */
 #define CW_DEC_PROFILE 8          /* direct launches with a CUDA event after every kernel; read with cw_decode_profile */
 size_t cw_decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new);

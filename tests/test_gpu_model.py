@@ -121,3 +121,26 @@ def test_free_running_greedy_and_graph_equivalence(engine, tiny):
         if first < T:  # a divergence from the fp32 oracle is only legitimate at a near-tie of the oracle's scores
             assert margin[bi, first] < 0.3, (bi, first, margin[bi, first])
     assert n_match >= B * 2
+
+
+def test_megakernel_matches_per_operator_kernels(engine, tiny):
+    """The persistent cooperative step kernel (default for B <= 8) and the one-kernel-per-operator path agree: identical
+    token ids under teacher forcing, processed scores within 2e-2, alignment probabilities within 1e-4."""
+    from crisperwhisper_b200 import _lib as L
+    xkv, _ = engine.encode(_feats_tm(tiny["feats"]).cuda())
+    B = tiny["feats"].shape[0]
+    p = torch.tensor([[257, 258, 359]] * B, dtype=torch.int32).cuda()
+    T = 20
+    a = engine.decode(xkv, p, T, flags=L.CW_DEC_SUPPRESS_EOS, want_logits=True)
+    engine.sync()
+    forced = a["tokens"][:, 3:3 + T].contiguous()
+    b = engine.decode(xkv, p, T, flags=L.CW_DEC_SUPPRESS_EOS | L.CW_DEC_NO_MEGA, forced=forced, want_logits=True)
+    c = engine.decode(xkv, p, T, flags=L.CW_DEC_SUPPRESS_EOS | L.CW_DEC_NO_GRAPH, forced=forced, want_logits=True)
+    engine.sync()
+    la, lb, lc = a["logits"].cpu().numpy(), b["logits"].cpu().numpy(), c["logits"].cpu().numpy()
+    fin = np.isfinite(la)
+    assert np.array_equal(fin, np.isfinite(lb))
+    assert np.abs(la[fin] - lb[fin]).max() < 2e-2
+    assert np.array_equal(la, lc, equal_nan=True), "megakernel: graph replay and direct launch must be bit-identical"
+    assert np.abs(a["align"].cpu().numpy()[:, :, : T - 1] - b["align"].cpu().numpy()[:, :, : T - 1]).max() < 1e-4
+    assert np.array_equal(a["lengths"].cpu().numpy(), b["lengths"].cpu().numpy())
