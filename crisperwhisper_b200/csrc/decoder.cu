@@ -19,6 +19,7 @@
 //   sample_kernel       suppress lists + timestamp rules + fp32 log-softmax rule + argmax + EOS bookkeeping
 // One decode step is captured once into a CUDA graph; the position lives in device memory, so the same graph is
 // replayed for every step (cudaGraphLaunch), with the host polling the "all finished" counter every 16 steps.
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -663,7 +664,7 @@ void decode_state_free(cw_ctx* ctx) {
 struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
-  float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar;
+  float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg;
 };
 
 static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
@@ -687,6 +688,7 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.xscore = (float*)take((size_t)B * m.n_heads * m.n_audio_ctx * 4);
   t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
   t.bar = (unsigned int*)take(256);
+  t.dbg = (unsigned long long*)take(32 * 8);
   if (o) *o = t;
   return a.off + 256;
 }
@@ -850,6 +852,7 @@ static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv,
   p.st = bf.st; p.seq = bf.seq; p.xkv = xkv; p.align_map = ctx->d_align_map; p.align_out = align_out;
   p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
   p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.bar = bf.bar;
+  p.dbg = getenv("CW_MEGA_DEBUG") ? bf.dbg : nullptr;
   SampleParams& sp = p.sp;
   sp.logits = bf.logits; sp.suppress = ctx->d_suppress; sp.seq = bf.seq; sp.seq_ld = m.n_text_ctx;
   sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
@@ -872,9 +875,10 @@ static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv,
 }
 
 __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
-                                int eos, unsigned int* xcount, int n_xcount, unsigned int* bar) {
+                                int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) { st->pos = 0; st->n_finished = 0; *bar = 0u; }
+  if (i < 32) dbg[i] = 0ull;
   if (i < n_xcount) xcount[i] = 0u;
   if (i < B) finished[i] = 0;
   if (i < B * seq_ld) {
@@ -914,7 +918,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
 
   int n_init = B * m.n_text_ctx;
   dec_init_kernel<<<(n_init + 255) / 256, 256, 0, st>>>(bf.st, bf.finished, bf.seq, m.n_text_ctx, prompt, n_prompt, B,
-                                                        m.eos_id, bf.xcount, B * m.n_heads, bf.bar);
+                                                        m.eos_id, bf.xcount, B * m.n_heads, bf.bar, bf.dbg);
   CW_CHECK_LAUNCH("dec_init_kernel");
   ctx->launches += 1;
 
@@ -987,6 +991,16 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
     }
   }
   if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
+  if (use_mega && getenv("CW_MEGA_DEBUG")) {
+    unsigned long long h[32];
+    CW_CUDA(cudaStreamSynchronize(st));
+    CW_CUDA(cudaMemcpy(h, bf.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    static const char* nm[] = {"embed", "qkv", "self_attn", "o_proj", "q_cross", "cross_attn", "oc_proj", "fc1", "fc2", "logits"};
+    fprintf(stderr, "[CW_MEGA_DEBUG] CTA0 ns per step (compute / barrier wait), %d steps\n", total_steps);
+    for (int i = 0; i < 10; ++i)
+      fprintf(stderr, "  %-10s %9.0f / %9.0f\n", nm[i], (double)h[2 * i] / total_steps, (double)h[2 * i + 1] / total_steps);
+    fprintf(stderr, "  %-10s %9.0f\n", "sample", (double)h[20] / total_steps);
+  }
   dec_finish_kernel<<<B, 128, 0, st>>>(bf.seq, m.n_text_ctx, n_prompt, n_prompt + max_new, m.eos_id, tokens_out, len_out, B,
                                        steps_done);
   CW_CHECK_LAUNCH("dec_finish_kernel");

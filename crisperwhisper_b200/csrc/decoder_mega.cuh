@@ -36,6 +36,7 @@ struct MegaParams {
   float* xscore;             // [B*H][F] exp(score - m_split)
   unsigned int* xcount;      // [B*H]
   unsigned int* bar;         // grid barrier counter
+  unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
   SampleParams sp;
 };
 
@@ -331,6 +332,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
   const unsigned int G = gridDim.x;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int pos = p.st->pos;  // written by the previous launch only
+  unsigned long long t_prev = 0;
+  auto tick = [&](int slot) {  // CTA 0 / thread 0: accumulate elapsed ns into dbg[slot]
+    if (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (slot >= 0) p.dbg[slot] += t - t_prev;
+      t_prev = t;
+    }
+  };
+  tick(-1);
 
   // ---- embed: x[b] = tok_emb[token] + pos_emb[pos] ---------------------------------------------------------
   {
@@ -342,7 +353,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
       p.x[i] = __bfloat162float(emb[(size_t)tok * d + k]) + ptab[k];
     }
   }
+  tick(0);
   grid_barrier(p.bar, G);
+  tick(1);
 
   const size_t cache_l = (size_t)B * p.n_ctx * d;
   const size_t xkv_l = (size_t)B * F * 2 * d;
@@ -356,7 +369,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
     __syncthreads();
     o.out_f32 = p.qbuf; o.out_bf16 = nullptr; o.kcache = kc; o.vcache = vc; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
     CW_MEGA_GEMV(8, EPI_QKV, (const bf16*)L[CW_DL_WQKV], (const float*)L[CW_DL_BQKV], 3 * d, d, XSd);
+    tick(2);
     grid_barrier(p.bar, G);
+    tick(3);
     // P2: causal self-attention, one 8-warp group per (sample, head)
     {
       const int grp = warp >> 3, gtid = tid & 255;
@@ -371,19 +386,25 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
         if (gtid < 64) p.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(base[64 + 448 + 8 + gtid] / l_);
       }
     }
+    tick(4);
     grid_barrier(p.bar, G);
+    tick(5);
     // P3: x += Wo . attn + bo
     stage_bf16(xs, XSd, p.attn, d, B);
     __syncthreads();
     o.out_f32 = p.x;
     CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WO], (const float*)L[CW_DL_BO], d, d, XSd);
+    tick(6);
     grid_barrier(p.bar, G);
+    tick(7);
     // P4: q_c = Wqc . LN2(x)
     stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN2_G], (const float*)L[CW_DL_LN2_B], d, B);
     __syncthreads();
     o.out_f32 = p.qbuf;
     CW_MEGA_GEMV(8, EPI_F32, (const bf16*)L[CW_DL_WQC], (const float*)L[CW_DL_BQC], d, d, XSd);
+    tick(8);
     grid_barrier(p.bar, G);
+    tick(9);
     // P5: cross-attention, (sample, head) x 3 frame splits, 4-warp groups
     {
       const int grp = warp >> 2, gtid = tid & 127;
@@ -443,25 +464,33 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
         }
       }
     }
+    tick(10);
     grid_barrier(p.bar, G);
+    tick(11);
     // P6: x += Woc . attn + boc
     stage_bf16(xs, XSd, p.attn, d, B);
     __syncthreads();
     o.out_f32 = p.x;
     CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WOC], (const float*)L[CW_DL_BOC], d, d, XSd);
+    tick(12);
     grid_barrier(p.bar, G);
+    tick(13);
     // P7: h = GELU(W1 . LN3(x) + b1)
     stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN3_G], (const float*)L[CW_DL_LN3_B], d, B);
     __syncthreads();
     o.out_bf16 = p.hbuf;
     CW_MEGA_GEMV(4, EPI_GELU_BF16, (const bf16*)L[CW_DL_W1], (const float*)L[CW_DL_B1], p.ffn, d, XSd);
+    tick(14);
     grid_barrier(p.bar, G);
+    tick(15);
     // P8: x += W2 . h + b2
     stage_bf16(xs, XSf, p.hbuf, p.ffn, B);
     __syncthreads();
     o.out_f32 = p.x;
     CW_MEGA_GEMV(16, EPI_RESID, (const bf16*)L[CW_DL_W2], (const float*)L[CW_DL_B2], d, p.ffn, XSf);
+    tick(16);
     grid_barrier(p.bar, G);
+    tick(17);
   }
   // ---- final LayerNorm + tied proj_out --------------------------------------------------------------------
   {
@@ -471,8 +500,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams
     o.out_f32 = p.logits; o.out_bf16 = nullptr; o.kcache = nullptr; o.vcache = nullptr; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
     CW_MEGA_GEMV(4, EPI_F32, (const bf16*)p.W[CW_W_TOK_EMB], (const float*)nullptr, p.Vp, d, XSd);
   }
+  tick(18);
   grid_barrier(p.bar, G);
+  tick(19);
   if ((int)blockIdx.x < B) mega_sample(p.sp, blockIdx.x, pos, sh, sh_i, sh_v);
+  tick(20);
   // the position advances once every CTA has read `pos` (all did, at kernel entry, before the first barrier)
   if (blockIdx.x == 0 && tid == 0) p.st->pos = pos + 1;
 }
