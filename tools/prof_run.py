@@ -21,7 +21,8 @@ if "encode" in what or "decode" in what:
     xkv, _ = eng.encode(tm)
 if "decode" in what:
     prompt = torch.tensor([[50258, 50259, 50360]] * B, dtype=torch.int32, device="cuda")
-    out = eng.decode(xkv, prompt, T, flags=L.CW_DEC_SUPPRESS_EOS | L.CW_DEC_NO_GRAPH)
+    mega = 0 if os.environ.get("PROF_MEGA", "0") == "1" else L.CW_DEC_NO_MEGA
+    out = eng.decode(xkv, prompt, T, flags=L.CW_DEC_SUPPRESS_EOS | L.CW_DEC_NO_GRAPH | mega)
 if "align" in what:
     al = torch.softmax(torch.randn(N5, 20, 448, 1500, device="cuda") * 3, -1)
     eng.align(al, torch.full((N5,), 448, dtype=torch.int32), torch.full((N5,), 1500, dtype=torch.int32), 7)
