@@ -664,7 +664,7 @@ void decode_state_free(cw_ctx* ctx) {
 struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
-  float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg;
+  float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg; void* prog;
 };
 
 static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
@@ -689,6 +689,7 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
   t.bar = (unsigned int*)take(256);
   t.dbg = (unsigned long long*)take(32 * 8);
+  t.prog = take((size_t)(8 * m.dec_layers + 4) * 128);
   if (o) *o = t;
   return a.off + 256;
 }
@@ -839,9 +840,9 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   return CW_OK;
 }
 
-// one cooperative launch for the whole step
-static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
-                             const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
+// fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
+static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
+                              const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
   const ModelDesc& m = ctx->md;
   MegaParams p;
   memset(&p, 0, sizeof(p));
@@ -858,6 +859,53 @@ static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv,
   sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
   sp.max_new = max_new; sp.eos = m.eos_id; sp.no_ts = m.no_timestamps_id; sp.max_initial_ts = m.max_initial_timestamp_index;
   sp.flags = flags; sp.forced = forced; sp.logits_out = logits_out; sp.argmax_out = argmax_out;
+  // the step as a program of phases
+  static_assert(sizeof(PhaseDesc) <= 128, "PhaseDesc grew beyond its workspace slot");
+  std::vector<PhaseDesc> prog;
+  auto gemv_ph = [&](int slot, int epi, int kmax, int N, int K, const void* Wm, const void* bias, const void* g, const void* bt,
+                     const float* src_f32, const bf16* src_bf16, float* out_f32, bf16* out_bf16, bf16* kcp, bf16* vcp) {
+    PhaseDesc d;
+    memset(&d, 0, sizeof(d));
+    d.type = PH_GEMV; d.epi = epi; d.kmax = kmax; d.N = N; d.K = K; d.ln = (g != nullptr); d.dbg_slot = slot;
+    d.W = (const bf16*)Wm; d.bias = (const float*)bias; d.ln_g = (const float*)g; d.ln_b = (const float*)bt;
+    d.src_f32 = src_f32; d.src_bf16 = src_bf16; d.out_f32 = out_f32; d.out_bf16 = out_bf16; d.kcache = kcp; d.vcache = vcp;
+    prog.push_back(d);
+  };
+  auto simple_ph = [&](int type, int slot, int l) {
+    PhaseDesc d;
+    memset(&d, 0, sizeof(d));
+    d.type = type; d.l = l; d.dbg_slot = slot;
+    prog.push_back(d);
+  };
+  const int d_ = m.d_model;
+  const size_t cache_l = (size_t)B * m.n_text_ctx * d_;
+  simple_ph(PH_EMBED, 0, 0);
+  for (int l = 0; l < m.dec_layers; ++l) {
+    const void** Lw = ctx->w + CW_W_GLOBAL_COUNT + (size_t)m.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
+    gemv_ph(1, EPI_QKV, 8, 3 * d_, d_, Lw[CW_DL_WQKV], Lw[CW_DL_BQKV], Lw[CW_DL_LN1_G], Lw[CW_DL_LN1_B], bf.x, nullptr, bf.qbuf, nullptr,
+            bf.kc + l * cache_l, bf.vc + l * cache_l);
+    simple_ph(PH_SELF_ATTN, 2, l);
+    gemv_ph(3, EPI_RESID, 8, d_, d_, Lw[CW_DL_WO], Lw[CW_DL_BO], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
+    gemv_ph(4, EPI_F32, 8, d_, d_, Lw[CW_DL_WQC], Lw[CW_DL_BQC], Lw[CW_DL_LN2_G], Lw[CW_DL_LN2_B], bf.x, nullptr, bf.qbuf, nullptr, nullptr, nullptr);
+    simple_ph(PH_CROSS_ATTN, 5, l);
+    gemv_ph(6, EPI_RESID, 8, d_, d_, Lw[CW_DL_WOC], Lw[CW_DL_BOC], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
+    gemv_ph(7, EPI_GELU_BF16, 4, m.ffn_dim, d_, Lw[CW_DL_W1], Lw[CW_DL_B1], Lw[CW_DL_LN3_G], Lw[CW_DL_LN3_B], bf.x, nullptr, nullptr, bf.hbuf, nullptr, nullptr);
+    gemv_ph(8, EPI_RESID, 16, d_, m.ffn_dim, Lw[CW_DL_W2], Lw[CW_DL_B2], nullptr, nullptr, nullptr, bf.hbuf, bf.x, nullptr, nullptr, nullptr);
+  }
+  gemv_ph(9, EPI_F32, 4, m.vocab_padded, d_, ctx->w[CW_W_TOK_EMB], nullptr, ctx->w[CW_W_DEC_LNF_G], ctx->w[CW_W_DEC_LNF_B], bf.x, nullptr,
+          bf.logits, nullptr, nullptr, nullptr);
+  CW_REQUIRE(prog.size() <= (size_t)(8 * m.dec_layers + 4), CW_ERR_INVALID, "decode program too long");
+  CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice, st));
+  p.prog = (const PhaseDesc*)bf.prog;
+  p.n_phases = (int)prog.size();
+  CW_CUDA(cudaMemcpyToSymbolAsync(c_mp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
+  CW_CUDA(cudaStreamSynchronize(st));  // `p` is a stack object
+  return CW_OK;
+}
+
+// one cooperative launch for the whole step
+static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
+  const ModelDesc& m = ctx->md;
   const int kmax = m.ffn_dim > m.d_model ? m.ffn_dim : m.d_model;
   const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4;
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
@@ -869,7 +917,7 @@ static int enqueue_step_mega(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv,
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CW_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel, p));
+  CW_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel));
   ctx->launches += 1;
   return CW_OK;
 }
@@ -929,7 +977,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   // B <= 8: the whole step is one persistent cooperative kernel; otherwise (or on request) one kernel per operator
   const bool use_mega = (B <= 8) && (m.d_model <= 1280) && !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
   auto step_fn = [&](cw_ctx* c) -> int {
-    if (use_mega) return enqueue_step_mega(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+    if (use_mega) return enqueue_step_mega(c, st);
     return enqueue_step(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
   };
   StepProf prof;
@@ -964,6 +1012,10 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
     }
   }
   const long long per_step = use_mega ? 1 : 5 + 8LL * m.dec_layers;  // kernels in one step
+  if (use_mega) {
+    rc = mega_upload_params(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+    if (rc != CW_OK) return rc;
+  }
   int steps_done = 0;  // generated tokens
   int h_state[4] = {0, 0, 0, 0};
   if (profile) {

@@ -20,6 +20,17 @@ static constexpr int kMegaWarps = 16;
 static constexpr int kXSplit = 3;          // cross-attention frame splits per (sample, head)
 static constexpr int kXFrames = 500;       // frames per split (1500 / 3)
 
+enum { PH_EMBED = 0, PH_GEMV = 1, PH_SELF_ATTN = 2, PH_CROSS_ATTN = 3 };
+
+// One phase of the decode step. The persistent kernel is an interpreter over an array of these: every operand comes
+// from memory at run time, so nothing of one phase stays live in registers during another.
+struct PhaseDesc {
+  int type, epi, kmax, N, K, l, ln, dbg_slot;
+  const bf16* W; const float* bias; const float* ln_g; const float* ln_b;
+  const float* src_f32; const bf16* src_bf16;
+  float* out_f32; bf16* out_bf16; bf16* kcache; bf16* vcache;
+};
+
 struct MegaParams {
   const void* const* W;      // device copy of the weight pointer table
   int enc_layers, dec_layers, d, n_heads, ffn, Vp, n_ctx, F, B;
@@ -37,6 +48,7 @@ struct MegaParams {
   unsigned int* xcount;      // [B*H]
   unsigned int* bar;         // grid barrier counter
   unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
+  const struct PhaseDesc* prog; int n_phases;   // the step as a list of phases (built on the host once per call)
   SampleParams sp;
 };
 
@@ -57,7 +69,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
       unsigned int v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if ((int)(v - target) >= 0) break;
-      if (++spins > (1u << 26)) { printf("libcrisper decode: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+      if (++spins > (1u << 26)) __trap();
     }
     __threadfence();
   }
@@ -65,7 +77,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
 }
 
 // ---- activation staging: rows of B samples -> bf16 [8][K+32] in smem --------------------------------------
-__device__ __noinline__ void stage_ln(bf16* xs, int XS, const float* x, const float* g, const float* bt, int K, int B) {
+__device__ __forceinline__ void stage_ln(bf16* xs, int XS, const float* x, const float* g, const float* bt, int K, int B) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = K >> 7;
   if (warp < 8) {
@@ -110,7 +122,7 @@ __device__ __noinline__ void stage_ln(bf16* xs, int XS, const float* x, const fl
   }
 }
 
-__device__ __noinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
+__device__ __forceinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
   const int vec_per_row = K >> 3;
   const int total = 8 * vec_per_row;
   for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kMegaThreads) {
@@ -135,14 +147,6 @@ __device__ __noinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K
   }
 }
 
-// pick the widest K-split (<= kMax warps per tile) whose slice is a multiple of 32
-#define CW_MEGA_GEMV(kMax, EPI, Wp, bias, N, K, XS)                                                          \
-  do {                                                                                                       \
-    if ((kMax) >= 16 && (K) % 512 == 0) mega_gemv<16, EPI>(Wp, bias, N, K, B, xs, XS, red, o);               \
-    else if ((kMax) >= 8 && (K) % 256 == 0) mega_gemv<8, EPI>(Wp, bias, N, K, B, xs, XS, red, o);            \
-    else mega_gemv<4, EPI>(Wp, bias, N, K, B, xs, XS, red, o);                                               \
-  } while (0)
-
 struct GemvOut {
   float* out_f32;   // F32 / RESID / QKV(q)
   bf16* out_bf16;   // GELU_BF16
@@ -152,11 +156,10 @@ struct GemvOut {
 
 // Projection phase: all 16-row tiles of W [N, K]; KW warps per tile, 16/KW tiles in flight per CTA.
 // Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
-template <int KW, int EPI>
-__device__ __noinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
-                                          const bf16* xs, int XS, float* red, const GemvOut& o) {
-  constexpr int S = kMegaWarps / KW;      // concurrent tiles per CTA
-  constexpr int GT = KW * 32;             // threads per group
+__device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
+                                          const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi) {
+  const int S = kMegaWarps / KW;        // concurrent tiles per CTA
+  const int GT = KW * 32;               // threads per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp / KW, wl = warp - grp * KW;
   const int gtid = threadIdx.x - grp * GT;
@@ -202,16 +205,15 @@ __device__ __noinline__ void mega_gemv(const bf16* __restrict__ W, const float* 
       const int r = gtid & 15, bcol = gtid >> 4;
       if (bcol < B) {
         float v = 0.f;
-#pragma unroll
         for (int w = 0; w < KW; ++w) v += gred[w * 128 + r * 8 + bcol];
         const int n = n0 + r;
         if (bias) v += __ldg(bias + n);
-        if (EPI == EPI_F32) {
+        if (epi == EPI_F32) {
           o.out_f32[(size_t)bcol * N + n] = v;
-        } else if (EPI == EPI_RESID) {
+        } else if (epi == EPI_RESID) {
           float* px = o.out_f32 + (size_t)bcol * N + n;
           *px = ld_cg(px) + v;
-        } else if (EPI == EPI_GELU_BF16) {
+        } else if (epi == EPI_GELU_BF16) {
           o.out_bf16[(size_t)bcol * N + n] = __float2bfloat16(gelu_erf_d(v));
         } else {
           const int d = o.d;
@@ -228,10 +230,9 @@ __device__ __noinline__ void mega_gemv(const bf16* __restrict__ W, const float* 
 // Attention of one query row over n rows by a group of GT threads (8 threads per row). Returns, in smem/regs:
 // sp[j] = exp(score_j - m), local max m and sum l (broadcast to every thread), acc -> so then out[64] in so[0][..].
 template <int GT, int UN>
-__device__ __noinline__ void group_attend(const float* __restrict__ q64, const bf16* __restrict__ kb,
-                                             const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
-                                             float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/, float& m_out,
-                                             float& l_out) {
+__device__ __forceinline__ float2 group_attend(const float* __restrict__ q64, const bf16* __restrict__ kb,
+                                            const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
+                                            float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/) {
   constexpr int G = GT / 8;
   const int sub = gtid & 7, grp = gtid >> 3;
   if (gtid < 64) sq[gtid] = ld_cg(q64 + gtid);
@@ -275,7 +276,6 @@ __device__ __noinline__ void group_attend(const float* __restrict__ q64, const b
   float tot = 0.f;
 #pragma unroll
   for (int w = 0; w < GT / 32; ++w) tot += sred[w];
-  m_out = mx; l_out = tot;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -311,201 +311,147 @@ __device__ __noinline__ void group_attend(const float* __restrict__ q64, const b
     so[gtid] = v;  // row 0, column gtid (each thread only overwrites the element it just finished reading in its column)
   }
   named_bar(bar_id, GT);
+  return make_float2(mx, tot);
 }
 
-__device__ __noinline__ void mega_sample(const SampleParams& sp, int b, int pos, float* sh, int* sh_i, float* sh_v) {
-  sample_body(sp, b, pos, sh, sh_i, sh_v);
+// The step parameters live in constant memory (copied once per cw_decode_greedy call).
+__constant__ MegaParams c_mp;
+
+extern __shared__ __align__(16) unsigned char msm[];
+// dynamic smem: xs bf16 [8][ffn+32] | red f32 [16][128]; the attention scratch aliases xs (phases never overlap in a CTA)
+__device__ __forceinline__ bf16* sm_xs() { return reinterpret_cast<bf16*>(msm); }
+__device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(msm + (size_t)8 * (c_mp.ffn + 32) * 2); }
+__device__ __forceinline__ float* sm_attn() { return reinterpret_cast<float*>(msm); }
+
+__device__ __forceinline__ void ph_embed(int pos) {
+  const int d = c_mp.d;
+  const bf16* emb = (const bf16*)c_mp.W[CW_W_TOK_EMB];
+  const float* ptab = (const float*)c_mp.W[CW_W_DEC_POS] + (size_t)pos * d;
+  for (int i = blockIdx.x * kMegaThreads + threadIdx.x; i < c_mp.B * d; i += gridDim.x * kMegaThreads) {
+    const int b = i / d, k = i - b * d;
+    const int tok = c_mp.seq[(size_t)b * c_mp.n_ctx + pos];
+    c_mp.x[i] = __bfloat162float(emb[(size_t)tok * d + k]) + ptab[k];
+  }
 }
 
-// dynamic smem: xs bf16 [8][ffn+32] | red f32 [16][128] | attention scratch (aliases xs)
-__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel(MegaParams p) {
-  extern __shared__ __align__(16) unsigned char msm[];
+__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
+  const int N = D->N, K = D->K, XS = K + 32;
+  if (D->ln) stage_ln(sm_xs(), XS, D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
+  else stage_bf16(sm_xs(), XS, D->src_bf16, K, c_mp.B);
+  __syncthreads();
+  GemvOut o;
+  o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
+  o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
+  const int kmax = D->kmax;
+  const int KW = (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
+  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi);
+}
+
+__device__ __forceinline__ void ph_self_attn(int l, int pos) {
+  const int d = c_mp.d, H = c_mp.n_heads;
+  const int warp = threadIdx.x >> 5;
+  const int grp = warp >> 3, gtid = threadIdx.x & 255;
+  const int task = blockIdx.x + gridDim.x * grp;
+  if (task >= c_mp.B * H) return;
+  const size_t cache_l = (size_t)c_mp.B * c_mp.n_ctx * d;
+  const int b = task / H, h = task - b * H;
+  float* base = sm_attn() + grp * 4096;     // sq[64] | sp[448] | sred[8] | so[32*65]
+  const bf16* kc = c_mp.kc + l * cache_l + (size_t)b * c_mp.n_ctx * d + h * 64;
+  const bf16* vc = c_mp.vc + l * cache_l + (size_t)b * c_mp.n_ctx * d + h * 64;
+  const float2 ml = group_attend<256, 4>(c_mp.qbuf + (size_t)b * d + h * 64, kc, vc, (size_t)d, pos + 1, gtid, 1 + grp, base,
+                                         base + 64, base + 64 + 448, base + 64 + 448 + 8);
+  if (gtid < 64) c_mp.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(base[64 + 448 + 8 + gtid] / ml.y);
+}
+
+__device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
+  const int d = c_mp.d, H = c_mp.n_heads, F = c_mp.F;
+  const int warp = threadIdx.x >> 5;
+  const int grp = warp >> 2, gtid = threadIdx.x & 127;
+  const int sub_id = blockIdx.x + gridDim.x * grp;
+  if (sub_id >= c_mp.B * H * kXSplit) return;
+  float* base = sm_attn() + grp * 2048;     // sq[64] | sp[500] | sred[4] | so[16*65]
+  const int task = sub_id / kXSplit, split = sub_id - task * kXSplit;
+  const int b = task / H, h = task - b * H;
+  const int f0 = split * kXFrames;
+  const int nf = min(kXFrames, F - f0);
+  const size_t fstride = (size_t)2 * d;
+  const size_t xkv_l = (size_t)c_mp.B * F * 2 * d;
+  const bf16* kb = c_mp.xkv + l * xkv_l + ((size_t)b * F + f0) * fstride + h * 64;
+  float* sp = base + 64;
+  float* so = base + 64 + 500 + 4;
+  const float2 ml = group_attend<128, 8>(c_mp.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base, sp,
+                                         base + 64 + 500, so);
+  const int slot = c_mp.align_map[l * H + h];
+  float* part = c_mp.xpart + ((size_t)task * kXSplit + split) * 66;
+  if (gtid < 64) part[2 + gtid] = so[gtid];
+  if (gtid == 0) { part[0] = ml.x; part[1] = ml.y; }
+  if (slot >= 0) {
+    float* sc = c_mp.xscore + (size_t)task * F + f0;
+    for (int j = gtid; j < nf; j += 128) sc[j] = sp[j];
+  }
+  __threadfence();
+  named_bar(1 + grp, 128);
+  if (gtid == 0) {
+    const unsigned int old = atomicAdd(c_mp.xcount + task, 1u);
+    s_flag[grp] = (old == kXSplit - 1) ? 1 : 0;
+    if (old == kXSplit - 1) c_mp.xcount[task] = 0;
+  }
+  named_bar(1 + grp, 128);
+  if (s_flag[grp]) {  // last arriver: merge the three partial softmaxes
+    __threadfence();
+    const float* pt = c_mp.xpart + (size_t)task * kXSplit * 66;
+    static_assert(kXSplit == 3, "merge below is written for 3 splits");
+    const float m0 = ld_cg(pt), m1 = ld_cg(pt + 66), m2 = ld_cg(pt + 132);
+    const float l0 = ld_cg(pt + 1), l1 = ld_cg(pt + 67), l2 = ld_cg(pt + 133);
+    const float M = fmaxf(m0, fmaxf(m1, m2));
+    const float w0 = expf(m0 - M), w1 = expf(m1 - M), w2 = expf(m2 - M);
+    const float inv = 1.f / (l0 * w0 + l1 * w1 + l2 * w2);
+    if (gtid < 64) {
+      const float v = ld_cg(pt + 2 + gtid) * w0 + ld_cg(pt + 68 + gtid) * w1 + ld_cg(pt + 134 + gtid) * w2;
+      c_mp.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(v * inv);
+    }
+    const int s_row = pos - c_mp.n_prompt;
+    if (slot >= 0 && c_mp.align_out != nullptr && s_row >= 0 && s_row < c_mp.T_cap) {
+      float* dst = c_mp.align_out + (((size_t)b * c_mp.H_a + slot) * c_mp.T_cap + s_row) * F;
+      const float* sc = c_mp.xscore + (size_t)task * F;
+      for (int j = gtid; j < F; j += 128) dst[j] = ld_cg(sc + j) * (j < kXFrames ? w0 : (j < 2 * kXFrames ? w1 : w2)) * inv;
+    }
+  }
+}
+
+__device__ __forceinline__ void mega_tick(int slot, unsigned long long& t_prev) {
+  if (c_mp.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (slot >= 0) c_mp.dbg[slot] += t - t_prev;
+    t_prev = t;
+  }
+}
+
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
   __shared__ float sh[32];
   __shared__ int sh_i[32];
   __shared__ float sh_v[32];
   __shared__ int s_flag[4];
-  const int d = p.d, B = p.B, H = p.n_heads, F = p.F;
-  const int XSd = d + 32, XSf = p.ffn + 32;
-  bf16* xs = reinterpret_cast<bf16*>(msm);
-  float* red = reinterpret_cast<float*>(msm + (size_t)8 * XSf * 2);
-  float* ascr = reinterpret_cast<float*>(msm);  // attention scratch aliases xs (phases never overlap inside a CTA)
-  const unsigned int G = gridDim.x;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int pos = p.st->pos;  // written by the previous launch only
+  const int pos = c_mp.st->pos;  // written by the previous launch only
   unsigned long long t_prev = 0;
-  auto tick = [&](int slot) {  // CTA 0 / thread 0: accumulate elapsed ns into dbg[slot]
-    if (p.dbg != nullptr && blockIdx.x == 0 && tid == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (slot >= 0) p.dbg[slot] += t - t_prev;
-      t_prev = t;
-    }
-  };
-  tick(-1);
-
-  // ---- embed: x[b] = tok_emb[token] + pos_emb[pos] ---------------------------------------------------------
-  {
-    const bf16* emb = (const bf16*)p.W[CW_W_TOK_EMB];
-    const float* ptab = (const float*)p.W[CW_W_DEC_POS] + (size_t)pos * d;
-    for (int i = blockIdx.x * kMegaThreads + tid; i < B * d; i += G * kMegaThreads) {
-      const int b = i / d, k = i - b * d;
-      const int tok = p.seq[(size_t)b * p.n_ctx + pos];
-      p.x[i] = __bfloat162float(emb[(size_t)tok * d + k]) + ptab[k];
-    }
+  mega_tick(-1, t_prev);
+  const int n_ph = c_mp.n_phases;
+#pragma unroll 1
+  for (int ph = 0; ph < n_ph; ++ph) {
+    const PhaseDesc* D = c_mp.prog + ph;
+    const int type = D->type;
+    if (type == PH_GEMV) ph_gemv(D, pos);
+    else if (type == PH_CROSS_ATTN) ph_cross_attn(D->l, pos, s_flag);
+    else if (type == PH_SELF_ATTN) ph_self_attn(D->l, pos);
+    else ph_embed(pos);
+    const int slot = D->dbg_slot;
+    mega_tick(2 * slot, t_prev);
+    grid_barrier(c_mp.bar, gridDim.x);
+    mega_tick(2 * slot + 1, t_prev);
   }
-  tick(0);
-  grid_barrier(p.bar, G);
-  tick(1);
-
-  const size_t cache_l = (size_t)B * p.n_ctx * d;
-  const size_t xkv_l = (size_t)B * F * 2 * d;
-  for (int l = 0; l < p.dec_layers; ++l) {
-    const void* const* L = p.W + CW_W_GLOBAL_COUNT + (size_t)p.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
-    bf16* kc = p.kc + l * cache_l;
-    bf16* vc = p.vc + l * cache_l;
-    GemvOut o;
-    // P1: q, k, v = Wqkv . LN1(x)
-    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN1_G], (const float*)L[CW_DL_LN1_B], d, B);
-    __syncthreads();
-    o.out_f32 = p.qbuf; o.out_bf16 = nullptr; o.kcache = kc; o.vcache = vc; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
-    CW_MEGA_GEMV(8, EPI_QKV, (const bf16*)L[CW_DL_WQKV], (const float*)L[CW_DL_BQKV], 3 * d, d, XSd);
-    tick(2);
-    grid_barrier(p.bar, G);
-    tick(3);
-    // P2: causal self-attention, one 8-warp group per (sample, head)
-    {
-      const int grp = warp >> 3, gtid = tid & 255;
-      const int task = blockIdx.x + G * grp;
-      float* base = ascr + grp * 4096;     // sq[64] | sp[448] | sred[8] | so[32*65]
-      if (task < B * H) {
-        const int b = task / H, h = task - b * H;
-        float m_, l_;
-        group_attend<256, 4>(p.qbuf + (size_t)b * d + h * 64, kc + (size_t)b * p.n_ctx * d + h * 64,
-                             vc + (size_t)b * p.n_ctx * d + h * 64, (size_t)d, pos + 1, gtid, 1 + grp, base, base + 64,
-                             base + 64 + 448, base + 64 + 448 + 8, m_, l_);
-        if (gtid < 64) p.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(base[64 + 448 + 8 + gtid] / l_);
-      }
-    }
-    tick(4);
-    grid_barrier(p.bar, G);
-    tick(5);
-    // P3: x += Wo . attn + bo
-    stage_bf16(xs, XSd, p.attn, d, B);
-    __syncthreads();
-    o.out_f32 = p.x;
-    CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WO], (const float*)L[CW_DL_BO], d, d, XSd);
-    tick(6);
-    grid_barrier(p.bar, G);
-    tick(7);
-    // P4: q_c = Wqc . LN2(x)
-    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN2_G], (const float*)L[CW_DL_LN2_B], d, B);
-    __syncthreads();
-    o.out_f32 = p.qbuf;
-    CW_MEGA_GEMV(8, EPI_F32, (const bf16*)L[CW_DL_WQC], (const float*)L[CW_DL_BQC], d, d, XSd);
-    tick(8);
-    grid_barrier(p.bar, G);
-    tick(9);
-    // P5: cross-attention, (sample, head) x 3 frame splits, 4-warp groups
-    {
-      const int grp = warp >> 2, gtid = tid & 127;
-      const int sub_id = blockIdx.x + G * grp;
-      float* base = ascr + grp * 2048;     // sq[64] | sp[500] | sred[4] | so[16*65]
-      if (sub_id < B * H * kXSplit) {
-        const int task = sub_id / kXSplit, split = sub_id - task * kXSplit;
-        const int b = task / H, h = task - b * H;
-        const int f0 = split * kXFrames;
-        const int nf = min(kXFrames, F - f0);
-        const size_t fstride = (size_t)2 * d;
-        const bf16* kb = p.xkv + l * xkv_l + ((size_t)b * F + f0) * fstride + h * 64;
-        float m_, l_;
-        float* sp = base + 64;
-        float* so = base + 64 + 500 + 4;
-        group_attend<128, 8>(p.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base, sp, base + 64 + 500,
-                             so, m_, l_);
-        const int slot = p.align_map[l * H + h];
-        float* part = p.xpart + ((size_t)task * kXSplit + split) * 66;
-        if (gtid < 64) part[2 + gtid] = so[gtid];
-        if (gtid == 0) { part[0] = m_; part[1] = l_; }
-        if (slot >= 0) {
-          float* sc = p.xscore + (size_t)task * F + f0;
-          for (int j = gtid; j < nf; j += 128) sc[j] = sp[j];
-        }
-        __threadfence();
-        named_bar(1 + grp, 128);
-        if (gtid == 0) {
-          const unsigned int old = atomicAdd(p.xcount + task, 1u);
-          s_flag[grp] = (old == kXSplit - 1) ? 1 : 0;
-          if (old == kXSplit - 1) p.xcount[task] = 0;
-        }
-        named_bar(1 + grp, 128);
-        if (s_flag[grp]) {  // last arriver: merge the partial softmaxes
-          __threadfence();
-          const float* pt = p.xpart + (size_t)task * kXSplit * 66;
-          float mi[kXSplit], li[kXSplit];
-          float M = -INFINITY;
-#pragma unroll
-          for (int s = 0; s < kXSplit; ++s) { mi[s] = ld_cg(pt + s * 66); li[s] = ld_cg(pt + s * 66 + 1); M = fmaxf(M, mi[s]); }
-          float Lsum = 0.f, wi[kXSplit];
-#pragma unroll
-          for (int s = 0; s < kXSplit; ++s) { wi[s] = expf(mi[s] - M); Lsum += li[s] * wi[s]; }
-          const float inv = 1.f / Lsum;
-          if (gtid < 64) {
-            float v = 0.f;
-#pragma unroll
-            for (int s = 0; s < kXSplit; ++s) v += ld_cg(pt + s * 66 + 2 + gtid) * wi[s];
-            p.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(v * inv);
-          }
-          const int s_row = pos - p.n_prompt;
-          if (slot >= 0 && p.align_out != nullptr && s_row >= 0 && s_row < p.T_cap) {
-            float* dst = p.align_out + (((size_t)b * p.H_a + slot) * p.T_cap + s_row) * F;
-            const float* sc = p.xscore + (size_t)task * F;
-            for (int j = gtid; j < F; j += 128) dst[j] = ld_cg(sc + j) * wi[j / kXFrames] * inv;
-          }
-        }
-      }
-    }
-    tick(10);
-    grid_barrier(p.bar, G);
-    tick(11);
-    // P6: x += Woc . attn + boc
-    stage_bf16(xs, XSd, p.attn, d, B);
-    __syncthreads();
-    o.out_f32 = p.x;
-    CW_MEGA_GEMV(8, EPI_RESID, (const bf16*)L[CW_DL_WOC], (const float*)L[CW_DL_BOC], d, d, XSd);
-    tick(12);
-    grid_barrier(p.bar, G);
-    tick(13);
-    // P7: h = GELU(W1 . LN3(x) + b1)
-    stage_ln(xs, XSd, p.x, (const float*)L[CW_DL_LN3_G], (const float*)L[CW_DL_LN3_B], d, B);
-    __syncthreads();
-    o.out_bf16 = p.hbuf;
-    CW_MEGA_GEMV(4, EPI_GELU_BF16, (const bf16*)L[CW_DL_W1], (const float*)L[CW_DL_B1], p.ffn, d, XSd);
-    tick(14);
-    grid_barrier(p.bar, G);
-    tick(15);
-    // P8: x += W2 . h + b2
-    stage_bf16(xs, XSf, p.hbuf, p.ffn, B);
-    __syncthreads();
-    o.out_f32 = p.x;
-    CW_MEGA_GEMV(16, EPI_RESID, (const bf16*)L[CW_DL_W2], (const float*)L[CW_DL_B2], d, p.ffn, XSf);
-    tick(16);
-    grid_barrier(p.bar, G);
-    tick(17);
-  }
-  // ---- final LayerNorm + tied proj_out --------------------------------------------------------------------
-  {
-    stage_ln(xs, XSd, p.x, (const float*)p.W[CW_W_DEC_LNF_G], (const float*)p.W[CW_W_DEC_LNF_B], d, B);
-    __syncthreads();
-    GemvOut o;
-    o.out_f32 = p.logits; o.out_bf16 = nullptr; o.kcache = nullptr; o.vcache = nullptr; o.d = d; o.n_ctx = p.n_ctx; o.pos = pos;
-    CW_MEGA_GEMV(4, EPI_F32, (const bf16*)p.W[CW_W_TOK_EMB], (const float*)nullptr, p.Vp, d, XSd);
-  }
-  tick(18);
-  grid_barrier(p.bar, G);
-  tick(19);
-  if ((int)blockIdx.x < B) mega_sample(p.sp, blockIdx.x, pos, sh, sh_i, sh_v);
-  tick(20);
+  if ((int)blockIdx.x < c_mp.B) sample_body(c_mp.sp, blockIdx.x, pos, sh, sh_i, sh_v);
+  mega_tick(20, t_prev);
   // the position advances once every CTA has read `pos` (all did, at kernel entry, before the first barrier)
-  if (blockIdx.x == 0 && tid == 0) p.st->pos = pos + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) c_mp.st->pos = pos + 1;
 }
-
