@@ -57,27 +57,21 @@ __device__ __forceinline__ float4 ld_cg4(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ uint4 ld_cg16(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// Grid-wide barrier without atomics: CTA i publishes the barrier generation in flags[i]; warp 0 of every CTA polls all
-// flags (one coalesced 128-byte line per 32 CTAs). Generations grow monotonically over the whole decode call
-// (gen = (pos + 1) * 1024 + k), the flags are zeroed by dec_init_kernel. Bounded spin -> trap instead of a hung GPU.
-__device__ __forceinline__ void grid_barrier(unsigned int* flags, unsigned int nblocks, unsigned int gen) {
+// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel): one atomic per CTA, thread 0 polls.
+// (A flag-per-CTA barrier polled by a whole warp was measured 3x slower: the polling traffic competes with the data.)
+// Bounded spin -> trap instead of a hung GPU.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int /*gen*/) {
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    if (lane == 0) {
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(gen) : "memory");
-    }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(bar, 1u);
+    const unsigned int target = (old / nblocks + 1u) * nblocks;
     unsigned int spins = 0;
     while (true) {
-      bool ok = true;
-      for (unsigned int i = lane; i < nblocks; i += 32) {
-        unsigned int v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
-        ok = ok && ((int)(v - gen) >= 0);
-      }
-      if (__all_sync(0xffffffffu, ok)) break;
-      if (++spins > (1u << 24)) __trap();
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (++spins > (1u << 26)) __trap();
     }
     __threadfence();
   }
