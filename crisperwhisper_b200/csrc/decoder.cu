@@ -687,7 +687,7 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.xpart = (float*)take((size_t)B * m.n_heads * kXSplit * 66 * 4);
   t.xscore = (float*)take((size_t)B * m.n_heads * m.n_audio_ctx * 4);
   t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
-  t.bar = (unsigned int*)take(4096);  // one barrier flag per CTA
+  t.bar = (unsigned int*)take(256);
   t.dbg = (unsigned long long*)take(32 * 8);
   t.prog = take((size_t)(8 * m.dec_layers + 4) * 128);
   if (o) *o = t;
@@ -925,8 +925,7 @@ static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
 __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
                                 int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { st->pos = 0; st->n_finished = 0; }
-  if (i < 1024) bar[i] = 0u;
+  if (i == 0) { st->pos = 0; st->n_finished = 0; *bar = 0u; }
   if (i < 32) dbg[i] = 0ull;
   if (i < n_xcount) xcount[i] = 0u;
   if (i < B) finished[i] = 0;

@@ -57,10 +57,8 @@ __device__ __forceinline__ float4 ld_cg4(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ uint4 ld_cg16(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel): one atomic per CTA, thread 0 polls.
-// (A flag-per-CTA barrier polled by a whole warp was measured 3x slower: the polling traffic competes with the data.)
-// Bounded spin -> trap instead of a hung GPU.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int /*gen*/) {
+// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel). Bounded spin -> trap.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -127,11 +125,10 @@ __device__ __forceinline__ void stage_ln(bf16* xs, int XS, const float* x, const
 __device__ __forceinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
   const int vec_per_row = K >> 3;
   const int total = 8 * vec_per_row;
-  constexpr int SU = 10;  // K = 5120: every thread has all of its ten 16-byte loads in flight at once
-  for (int i0 = threadIdx.x; i0 < total; i0 += SU * kMegaThreads) {
-    uint4 v[SU];
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kMegaThreads) {
+    uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < SU; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * kMegaThreads;
       v[u] = make_uint4(0, 0, 0, 0);
       if (i < total) {
@@ -140,7 +137,7 @@ __device__ __forceinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, in
       }
     }
 #pragma unroll
-    for (int u = 0; u < SU; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * kMegaThreads;
       if (i < total) {
         const int b = i / vec_per_row, c = i - b * vec_per_row;
@@ -160,8 +157,7 @@ struct GemvOut {
 // Projection phase: all 16-row tiles of W [N, K]; KW warps per tile, 16/KW tiles in flight per CTA.
 // Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
 __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
-                                          const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi,
-                                          uint4 (&pa0)[5], uint4 (&pa1)[5], bool have_pre) {
+                                          const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi) {
   const int S = kMegaWarps / KW;        // concurrent tiles per CTA
   const int GT = KW * 32;               // threads per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,16 +179,11 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
     constexpr int U = 5;
     for (int c0 = 0; c0 < chunks; c0 += U) {
       uint4 a0[U], a1[U];
-      if (have_pre && c0 == 0) {  // first batch of the first tile was issued before the previous grid barrier
 #pragma unroll
-        for (int u = 0; u < U; ++u) { a0[u] = pa0[u]; a1[u] = pa1[u]; }
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (c0 + u < chunks) {
-            a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
-            a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
-          }
+      for (int u = 0; u < U; ++u) {
+        if (c0 + u < chunks) {
+          a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+          a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
         }
       }
 #pragma unroll
@@ -205,7 +196,6 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
         }
       }
     }
-    have_pre = false;
     myred[g * 8 + 2 * t] = acc[0];
     myred[g * 8 + 2 * t + 1] = acc[1];
     myred[(g + 8) * 8 + 2 * t] = acc[2];
@@ -344,36 +334,7 @@ __device__ __forceinline__ void ph_embed(int pos) {
   }
 }
 
-__device__ __forceinline__ int gemv_kw(const PhaseDesc* D) {
-  const int kmax = D->kmax, K = D->K;
-  return (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
-}
-
-// Issue the first weight batch of this warp's first tile of GEMV phase D (weights never change during decoding, so this
-// can run before the grid barrier that precedes the phase). Mirrors the index arithmetic of mega_gemv.
-__device__ __forceinline__ bool gemv_prefetch(const PhaseDesc* D, uint4 (&pa0)[5], uint4 (&pa1)[5]) {
-  const int KW = gemv_kw(D);
-  const int K = D->K;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp / KW, wl = warp - grp * KW;
-  const int g = lane >> 2, t = lane & 3;
-  const int tile = blockIdx.x + gridDim.x * grp;
-  if (tile >= (D->N >> 4)) return false;
-  const int kslice = K / KW;
-  const int chunks = kslice >> 5;
-  const bf16* w0 = D->W + (size_t)((tile << 4) + g) * K + wl * kslice + 8 * t;
-  const bf16* w1 = w0 + (size_t)8 * K;
-#pragma unroll
-  for (int u = 0; u < 5; ++u) {
-    if (u < chunks) {
-      pa0[u] = ldg_stream(w0 + (size_t)u * 32);
-      pa1[u] = ldg_stream(w1 + (size_t)u * 32);
-    }
-  }
-  return true;
-}
-
-__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos, uint4 (&pa0)[5], uint4 (&pa1)[5], bool have_pre) {
+__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
   const int N = D->N, K = D->K, XS = K + 32;
   if (D->ln) stage_ln(sm_xs(), XS, D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
   else stage_bf16(sm_xs(), XS, D->src_bf16, K, c_mp.B);
@@ -381,7 +342,9 @@ __device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos, uint4 (&pa0
   GemvOut o;
   o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
   o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
-  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, gemv_kw(D), D->epi, pa0, pa1, have_pre);
+  const int kmax = D->kmax;
+  const int KW = (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
+  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi);
 }
 
 __device__ __forceinline__ void ph_self_attn(int l, int pos) {
@@ -474,22 +437,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
   unsigned long long t_prev = 0;
   mega_tick(-1, t_prev);
   const int n_ph = c_mp.n_phases;
-  const unsigned int gen0 = (unsigned int)(pos + 1) * 1024u;
-  uint4 pa0[5], pa1[5];
-  bool have_pre = false;
 #pragma unroll 1
   for (int ph = 0; ph < n_ph; ++ph) {
     const PhaseDesc* D = c_mp.prog + ph;
     const int type = D->type;
-    if (type == PH_GEMV) ph_gemv(D, pos, pa0, pa1, have_pre);
+    if (type == PH_GEMV) ph_gemv(D, pos);
     else if (type == PH_CROSS_ATTN) ph_cross_attn(D->l, pos, s_flag);
     else if (type == PH_SELF_ATTN) ph_self_attn(D->l, pos);
     else ph_embed(pos);
-    have_pre = false;
-    if (ph + 1 < n_ph && D[1].type == PH_GEMV) have_pre = gemv_prefetch(D + 1, pa0, pa1);
     const int slot = D->dbg_slot;
     mega_tick(2 * slot, t_prev);
-    grid_barrier(c_mp.bar, gridDim.x, gen0 + (unsigned int)ph + 1u);
+    grid_barrier(c_mp.bar, gridDim.x);
     mega_tick(2 * slot + 1, t_prev);
   }
   if ((int)blockIdx.x < c_mp.B) sample_body(c_mp.sp, blockIdx.x, pos, sh, sh_i, sh_v);

@@ -144,3 +144,20 @@ def test_megakernel_matches_per_operator_kernels(engine, tiny):
     assert np.array_equal(la, lc, equal_nan=True), "megakernel: graph replay and direct launch must be bit-identical"
     assert np.abs(a["align"].cpu().numpy()[:, :, : T - 1] - b["align"].cpu().numpy()[:, :, : T - 1]).max() < 1e-4
     assert np.array_equal(a["lengths"].cpu().numpy(), b["lengths"].cpu().numpy())
+
+
+def test_eos_stops_and_pads(engine, tiny):
+    """without CW_DEC_SUPPRESS_EOS: rows stop at eos, are padded with eos, lengths include the eos (both decode paths)."""
+    from crisperwhisper_b200 import _lib as L
+    cfg = tiny["cfg"]
+    xkv, _ = engine.encode(_feats_tm(tiny["feats"]).cuda())
+    B = tiny["feats"].shape[0]
+    p = torch.tensor([[257, 258, 359]] * B, dtype=torch.int32).cuda()
+    forced = torch.full((B, 10), 70, dtype=torch.int32)
+    forced[0, 3] = cfg["eos_id"]
+    for fl in (0, L.CW_DEC_NO_MEGA):
+        out = engine.decode(xkv, p, 10, flags=fl, forced=forced.cuda())
+        engine.sync()
+        tok, ln = out["tokens"].cpu().numpy(), out["lengths"].cpu().numpy()
+        assert ln[0] == 3 + 4 and (tok[0, 7:] == cfg["eos_id"]).all()
+        assert ln[1] == 13
