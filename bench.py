@@ -130,7 +130,9 @@ def run_reference(args, rank, world):
     import torch
     from oracle import hf_harness as H
     from oracle import postprocess as PP
-    cores = os.cpu_count() or 1
+    # PyTorch's CPU kernels stop scaling (and then regress badly) beyond a few dozen threads on these small per-token
+    # operators: 805 s for one 24-token chunk with 128 threads vs tens of seconds with 16 — use at most 16 and say so
+    cores = min(os.cpu_count() or 1, args.ref_threads)
     torch.set_num_threads(cores)
     T = min(args.new_tokens, args.ref_tokens)
     t0 = time.time()
@@ -139,7 +141,7 @@ def run_reference(args, rank, world):
     heads = [[l, (7 * l) % 20] for l in range(12, 32)]
     # fixed-length single-pass decode on both arms: EOS and every timestamp token but <|0.00|> are suppressed, so the
     # sequence is <|0.00|> + T-1 text tokens and Whisper's seek loop finishes after one encoder/decoder pass
-    m = H.build_model(hf_cfg, seed=0, alignment_heads=heads, ids=ids, bf16_round=False,
+    m = H.build_model(hf_cfg, seed=0, alignment_heads=heads, ids=ids, bf16_round=False, fast_init=True,
                       suppress_tokens=[50257] + list(range(50366, 51866)))
     from crisperwhisper_b200 import weights as Wt
     tok = big_tokenizer(Wt.large_v3_config())
@@ -164,7 +166,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.ref_warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "reference CPU path, bounded sample of cfg2", "new_tokens": T, "batch_per_step": 1,
+            "config": {"workload": "reference CPU path, bounded sample of cfg2", "new_tokens": T, "batch_per_step": 1, "host_threads": cores,
                        "model": "whisper-large-v3 shape, random init", "build_s": round(build_s, 1)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -180,7 +182,8 @@ def main():
     ap.add_argument("--impl", default="crisper", choices=["crisper", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="30 s chunks per GPU per step (BASELINE cfg 2: 8)")
     ap.add_argument("--new-tokens", dest="new_tokens", type=int, default=445, help="decoded tokens per chunk (445 = n_text_ctx - prompt)")
-    ap.add_argument("--ref-tokens", dest="ref_tokens", type=int, default=24, help="decode length of the bounded CPU sample")
+    ap.add_argument("--ref-tokens", dest="ref_tokens", type=int, default=8, help="decode length of the bounded CPU sample")
+    ap.add_argument("--ref-threads", dest="ref_threads", type=int, default=16, help="host threads for the reference arm")
     ap.add_argument("--ref-warmup", dest="ref_warmup", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-stage microbenchmarks")
@@ -388,7 +391,8 @@ def main():
     if not args.no_cpu_baseline:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--new-tokens",
-                                  str(T), "--ref-tokens", str(args.ref_tokens)], capture_output=True, text=True, timeout=900,
+                                  str(T), "--ref-tokens", str(args.ref_tokens), "--ref-threads", str(args.ref_threads)],
+                                 capture_output=True, text=True, timeout=600,
                                  env={**os.environ, "RANK": "0", "WORLD_SIZE": "1", "CUDA_VISIBLE_DEVICES": ""})
             ref_line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
             cpu_baseline = ref_line["cpu_baseline"]

@@ -55,12 +55,26 @@ def large_v3_hf_config(median_filter_width: int = 7):
 
 def build_model(hf_config, seed: int = 0, alignment_heads: Optional[List[List[int]]] = None, ids: Optional[Dict] = None,
                 logit_scale: float = 1.0, max_new_tokens: Optional[int] = None, suppress_tokens=None,
-                begin_suppress_tokens=None, bf16_round: bool = True, pos_scale: float = 1.0):
+                begin_suppress_tokens=None, bf16_round: bool = True, pos_scale: float = 1.0, fast_init: bool = False):
     """Random-init model whose parameters are rounded to bf16 and upcast (so the fp32 oracle and the bf16 kernels
     share values, SURVEY §7 'hard parts'), with the generation_config fields Whisper's generate needs."""
     from transformers import WhisperForConditionalGeneration
     torch.manual_seed(seed)
-    m = WhisperForConditionalGeneration(hf_config).eval()
+    if fast_init:  # large models: skip HF's slow per-module init, fill the parameters directly (values are irrelevant for timing)
+        from transformers.initialization import no_init_weights
+        with no_init_weights():
+            m = WhisperForConditionalGeneration(hf_config).eval()
+        with torch.no_grad():
+            for name, p in m.named_parameters():
+                if p.dim() >= 2:
+                    p.normal_(0.0, 0.02)
+                elif name.endswith("layer_norm.weight") or name.endswith("layernorm.weight"):
+                    p.fill_(1.0)
+                else:
+                    p.zero_()
+            m.model.encoder.embed_positions.weight.copy_(torch.randn_like(m.model.encoder.embed_positions.weight) * 0.02)
+    else:
+        m = WhisperForConditionalGeneration(hf_config).eval()
     with torch.no_grad():
         if logit_scale != 1.0:  # enlarge the (tied) embedding to create logit margin between tokens
             m.model.decoder.embed_tokens.weight.mul_(logit_scale)
