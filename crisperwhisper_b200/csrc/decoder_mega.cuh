@@ -157,7 +157,8 @@ struct GemvOut {
 // Projection phase: all 16-row tiles of W [N, K]; KW warps per tile, 16/KW tiles in flight per CTA.
 // Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
 __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
-                                          const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi) {
+                                          const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi,
+                                          const bf16* __restrict__ direct /* bf16 [B, K] activations read straight from L2, or null */) {
   const int S = kMegaWarps / KW;        // concurrent tiles per CTA
   const int GT = KW * 32;               // threads per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -178,19 +179,25 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int U = 5;
     for (int c0 = 0; c0 < chunks; c0 += U) {
-      uint4 a0[U], a1[U];
+      uint4 a0[U], a1[U], xd[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c0 + u < chunks) {
           a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
           a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+          if (direct != nullptr) {  // B fragment of sample g straight from L2 (no smem staging, no CTA-wide sync)
+            xd[u] = make_uint4(0, 0, 0, 0);
+            if (g < B) xd[u] = ld_cg16(reinterpret_cast<const uint4*>(direct + (size_t)g * K + kbeg + (c0 + u) * 32 + 8 * t));
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c0 + u < chunks) {
           const int kk = kbeg + (c0 + u) * 32 + 8 * t;
-          const uint4 xb = *reinterpret_cast<const uint4*>(xs + (size_t)g * XS + kk);
+          uint4 xb;
+          if (direct != nullptr) xb = xd[u];
+          else xb = *reinterpret_cast<const uint4*>(xs + (size_t)g * XS + kk);
           mma16816(acc, a0[u].x, a1[u].x, a0[u].y, a1[u].y, xb.x, xb.y);
           mma16816(acc, a0[u].z, a1[u].z, a0[u].w, a1[u].w, xb.z, xb.w);
         }
@@ -231,22 +238,31 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
 // sp[j] = exp(score_j - m), local max m and sum l (broadcast to every thread), acc -> so then out[64] in so[0][..].
 template <int GT, int UN>
 __device__ __forceinline__ float2 group_attend(const float* __restrict__ q64, const bf16* __restrict__ kb,
-                                            const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
-                                            float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/) {
+                                               const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
+                                               float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/) {
   constexpr int G = GT / 8;
   const int sub = gtid & 7, grp = gtid >> 3;
+  // first K batch goes out before the query is fetched: K (cache / encoder rows) does not depend on this step's q
+  uint4 u[UN];
+#pragma unroll
+  for (int x = 0; x < UN; ++x) {
+    const int j = grp + G * x;
+    u[x] = make_uint4(0, 0, 0, 0);
+    if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+  }
   if (gtid < 64) sq[gtid] = ld_cg(q64 + gtid);
   named_bar(bar_id, GT);
   float qv[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e];
   for (int base = 0; base < n; base += G * UN) {
-    uint4 u[UN];
+    if (base > 0) {
 #pragma unroll
-    for (int x = 0; x < UN; ++x) {
-      const int j = base + grp + G * x;
-      u[x] = make_uint4(0, 0, 0, 0);
-      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+      for (int x = 0; x < UN; ++x) {
+        const int j = base + grp + G * x;
+        u[x] = make_uint4(0, 0, 0, 0);
+        if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
+      }
     }
 #pragma unroll
     for (int x = 0; x < UN; ++x) {
@@ -257,6 +273,13 @@ __device__ __forceinline__ float2 group_attend(const float* __restrict__ q64, co
       s += __shfl_xor_sync(0xffffffffu, s, 4);
       if (sub == 0 && j < n) sp[j] = s;
     }
+  }
+  // first V batch is issued now and lands while the softmax statistics are computed
+#pragma unroll
+  for (int x = 0; x < UN; ++x) {
+    const int j = grp + G * x;
+    u[x] = make_uint4(0, 0, 0, 0);
+    if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
   }
   named_bar(bar_id, GT);
   float lmax = -INFINITY;
@@ -280,12 +303,13 @@ __device__ __forceinline__ float2 group_attend(const float* __restrict__ q64, co
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   for (int base = 0; base < n; base += G * UN) {
-    uint4 u[UN];
+    if (base > 0) {
 #pragma unroll
-    for (int x = 0; x < UN; ++x) {
-      const int j = base + grp + G * x;
-      u[x] = make_uint4(0, 0, 0, 0);
-      if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
+      for (int x = 0; x < UN; ++x) {
+        const int j = base + grp + G * x;
+        u[x] = make_uint4(0, 0, 0, 0);
+        if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
+      }
     }
 #pragma unroll
     for (int x = 0; x < UN; ++x) {
@@ -336,15 +360,17 @@ __device__ __forceinline__ void ph_embed(int pos) {
 
 __device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
   const int N = D->N, K = D->K, XS = K + 32;
-  if (D->ln) stage_ln(sm_xs(), XS, D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
-  else stage_bf16(sm_xs(), XS, D->src_bf16, K, c_mp.B);
-  __syncthreads();
+  const bool ln = D->ln != 0;
+  if (ln) {
+    stage_ln(sm_xs(), XS, D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
+    __syncthreads();
+  }
   GemvOut o;
   o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
   o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
   const int kmax = D->kmax;
   const int KW = (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
-  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi);
+  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi, ln ? nullptr : D->src_bf16);
 }
 
 __device__ __forceinline__ void ph_self_attn(int l, int pos) {
