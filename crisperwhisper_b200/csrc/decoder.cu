@@ -840,6 +840,14 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   return CW_OK;
 }
 
+// Cross-barrier weight prefetch (cp.async into per-lane smem slots) is implemented but OFF by default: measured on B200
+// it costs more than it hides (2.83 vs 2.44 ms/step) — 20 LDGSTS per thread are ~1.3 us of issue time per phase, and
+// the 80 KB buffer shrinks L1. CW_MEGA_PREFETCH=1 enables it for experiments.
+static bool mega_prefetch_enabled() {
+  const char* e = getenv("CW_MEGA_PREFETCH");
+  return e != nullptr && e[0] == '1';
+}
+
 // fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
 static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
                               const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
@@ -898,6 +906,7 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
   CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice, st));
   p.prog = (const PhaseDesc*)bf.prog;
   p.n_phases = (int)prog.size();
+  p.prefetch = mega_prefetch_enabled() ? 1 : 0;
   CW_CUDA(cudaMemcpyToSymbolAsync(c_mp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
   CW_CUDA(cudaStreamSynchronize(st));  // `p` is a stack object
   return CW_OK;
@@ -907,7 +916,8 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
 static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
   const ModelDesc& m = ctx->md;
   const int kmax = m.ffn_dim > m.d_model ? m.ffn_dim : m.d_model;
-  const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4;
+  const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4 +
+                      (mega_prefetch_enabled() ? (size_t)kMegaWarps * 5 * 64 * 16 : 0);
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
   CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;

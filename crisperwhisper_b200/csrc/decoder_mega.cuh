@@ -48,7 +48,7 @@ struct MegaParams {
   unsigned int* xcount;      // [B*H]
   unsigned int* bar;         // grid barrier counter
   unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
-  const struct PhaseDesc* prog; int n_phases;   // the step as a list of phases (built on the host once per call)
+  const struct PhaseDesc* prog; int n_phases; int prefetch;   // the step as a list of phases (built on the host once per call)
   SampleParams sp;
 };
 
@@ -158,7 +158,9 @@ struct GemvOut {
 // Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
 __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
                                           const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi,
-                                          const bf16* __restrict__ direct /* bf16 [B, K] activations read straight from L2, or null */) {
+                                          const bf16* __restrict__ direct /* bf16 [B, K] activations read straight from L2, or null */,
+                                          const bool have_pre /* first batch of the first tile is already in smem */,
+                                          const uint4* pre_base) {
   const int S = kMegaWarps / KW;        // concurrent tiles per CTA
   const int GT = KW * 32;               // threads per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,11 +182,18 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
     constexpr int U = 5;
     for (int c0 = 0; c0 < chunks; c0 += U) {
       uint4 a0[U], a1[U], xd[U];
+      const bool from_smem = have_pre && c0 == 0 && tile == (int)(blockIdx.x + gridDim.x * grp);
+      const uint4* pb = pre_base + (size_t)warp * (U * 64) + lane;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c0 + u < chunks) {
-          a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
-          a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+          if (from_smem) {
+            a0[u] = pb[u * 64];
+            a1[u] = pb[u * 64 + 32];
+          } else {
+            a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+            a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
+          }
           if (direct != nullptr) {  // B fragment of sample g straight from L2 (no smem staging, no CTA-wide sync)
             xd[u] = make_uint4(0, 0, 0, 0);
             if (g < B) xd[u] = ld_cg16(reinterpret_cast<const uint4*>(direct + (size_t)g * K + kbeg + (c0 + u) * 32 + 8 * t));
@@ -346,6 +355,10 @@ extern __shared__ __align__(16) unsigned char msm[];
 __device__ __forceinline__ bf16* sm_xs() { return reinterpret_cast<bf16*>(msm); }
 __device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(msm + (size_t)8 * (c_mp.ffn + 32) * 2); }
 __device__ __forceinline__ float* sm_attn() { return reinterpret_cast<float*>(msm); }
+// weight prefetch buffer: [16 warps][5 chunks][2 row halves][32 lanes] x 16 B = 80 KB, every lane owns its slots
+__device__ __forceinline__ uint4* sm_pre() {
+  return reinterpret_cast<uint4*>(msm + (size_t)8 * (c_mp.ffn + 32) * 2 + (size_t)kMegaWarps * 128 * 4);
+}
 
 __device__ __forceinline__ void ph_embed(int pos) {
   const int d = c_mp.d;
@@ -358,7 +371,41 @@ __device__ __forceinline__ void ph_embed(int pos) {
   }
 }
 
-__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
+__device__ __forceinline__ int gemv_kw_of(const PhaseDesc* D) {
+  const int kmax = D->kmax, K = D->K;
+  return (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
+}
+
+// Start fetching (cp.async, no registers) the first weight batch of this warp's first tile of GEMV phase D into the
+// warp's slots of sm_pre(). Weights never change while decoding, so this is issued before the grid barrier that precedes
+// the phase and lands while the CTA waits / stages activations. Mirrors the index arithmetic of mega_gemv.
+__device__ __forceinline__ bool gemv_prefetch(const PhaseDesc* D) {
+  const int KW = gemv_kw_of(D);
+  const int K = D->K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp / KW, wl = warp - grp * KW;
+  const int g = lane >> 2, t = lane & 3;
+  const int tile = blockIdx.x + gridDim.x * grp;
+  if (tile >= (D->N >> 4)) return false;
+  const int kslice = K / KW;
+  const int chunks = kslice >> 5;
+  const bf16* w0 = D->W + (size_t)((tile << 4) + g) * K + wl * kslice + 8 * t;
+  const bf16* w1 = w0 + (size_t)8 * K;
+  uint4* pb = sm_pre() + (size_t)warp * (5 * 64) + lane;
+#pragma unroll
+  for (int u = 0; u < 5; ++u) {
+    if (u < chunks) {
+      const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(pb + u * 64);
+      const uint32_t s1 = (uint32_t)__cvta_generic_to_shared(pb + u * 64 + 32);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s0), "l"(w0 + (size_t)u * 32));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s1), "l"(w1 + (size_t)u * 32));
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  return true;
+}
+
+__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos, bool have_pre) {
   const int N = D->N, K = D->K, XS = K + 32;
   const bool ln = D->ln != 0;
   if (ln) {
@@ -368,9 +415,9 @@ __device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
   GemvOut o;
   o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
   o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
-  const int kmax = D->kmax;
-  const int KW = (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
-  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi, ln ? nullptr : D->src_bf16);
+  const int KW = gemv_kw_of(D);
+  if (have_pre) asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // each lane reads back only its own slots
+  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi, ln ? nullptr : D->src_bf16, have_pre, sm_pre());
 }
 
 __device__ __forceinline__ void ph_self_attn(int l, int pos) {
@@ -463,14 +510,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
   unsigned long long t_prev = 0;
   mega_tick(-1, t_prev);
   const int n_ph = c_mp.n_phases;
+  bool have_pre = false;
 #pragma unroll 1
   for (int ph = 0; ph < n_ph; ++ph) {
     const PhaseDesc* D = c_mp.prog + ph;
     const int type = D->type;
-    if (type == PH_GEMV) ph_gemv(D, pos);
+    if (type == PH_GEMV) ph_gemv(D, pos, have_pre);
     else if (type == PH_CROSS_ATTN) ph_cross_attn(D->l, pos, s_flag);
     else if (type == PH_SELF_ATTN) ph_self_attn(D->l, pos);
     else ph_embed(pos);
+    have_pre = false;
+    if (c_mp.prefetch && ph + 1 < n_ph && D[1].type == PH_GEMV) have_pre = gemv_prefetch(D + 1);
     const int slot = D->dbg_slot;
     mega_tick(2 * slot, t_prev);
     grid_barrier(c_mp.bar, gridDim.x);
