@@ -79,8 +79,9 @@ struct ReduceParams {
 template <int P>
 __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
   constexpr int W = 2 * P + 1;
-  constexpr int TC = kFT + 2 * P;
-  constexpr int TS = TC | 1;  // odd row stride: conflict-free for the (row, half) thread mapping below
+  constexpr int PA = (P + 1) & ~1;         // halo rounded up to an even count: tile rows start 8-byte aligned in HBM
+  constexpr int TC = kFT + 2 * PA;         // columns staged per row (a superset of the kFT + 2P the median needs)
+  constexpr int TS = TC + 2;               // even row stride (8-byte cp.async destinations); 2-way LDS conflicts at most
   constexpr int NV = kColsPerThr + 2 * P;
 
   const int n = blockIdx.x / p.tiles_per_utt;
@@ -90,9 +91,9 @@ __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
   const int f0 = tile_i * kFT;
   if (T <= 0 || f0 >= Fp) return;
   const bool do_filter = (Fp > P);  // generation_whisper.py:53-54
-  const int ts = f0 - P;            // global frame of tile-local column 0
-  const int lo = max(0, -ts);
-  const int hi = min(TC, Fp - ts);
+  const int ts = f0 - PA;           // global frame of tile-local column 0
+  const int lo = max(max(0, -ts), PA - P);                 // tile-local columns the median can touch and that exist
+  const int hi = min(min(TC, Fp - ts), TC - (PA - P));
   const int nblk = (T + 15) >> 4;
   const int T_pad = (p.T_max + 15) & ~15;
 
@@ -114,12 +115,41 @@ __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
   for (int k = 0; k < kColsPerThr; ++k) acc1s[k * nthr + tid] = 0.f;
   const float* src_n = p.align + (size_t)n * p.H * p.T_max * p.F_max;
 
+  // Loader: thread (r0 = tid / (TC/2), c = tid % (TC/2)) copies the 8-byte pair of columns (2c, 2c+1) of rows r0, r0+RPP, ...
+  // with cp.async (src-size zero-fill for pairs that straddle the end of the row) — one LDGSTS and two pointer bumps per
+  // pair instead of per-element index arithmetic. Rows of odd length (F_max odd) fall back to 4-byte copies.
+  constexpr int PPR = TC / 2;                       // pairs per row
+  const int RPP = nthr / PPR;                       // rows per pass
+  const bool pair_ok = ((p.F_max & 1) == 0);
   auto issue_loads = [&](int h, float* dst) {
     const float* src = src_n + (size_t)h * p.T_max * p.F_max;
-    const int total = T * TC;
-    for (int idx = tid; idx < total; idx += nthr) {
-      int r = idx / TC, lc = idx - r * TC;
-      if (lc >= lo && lc < hi) cp_async4(dst + r * TS + lc, src + (size_t)r * p.F_max + (ts + lc));
+    if (pair_ok) {
+      if (tid < RPP * PPR) {
+        const int r0 = tid / PPR, c2 = (tid - r0 * PPR) * 2;
+        const int g = ts + c2;                      // global column of the pair's first element
+        int nbytes = 0;
+        if (g >= 0 && g < Fp) nbytes = (g + 1 < Fp) ? 8 : 4;
+        if (g == -1) nbytes = 0;                    // cannot happen: ts is even and g steps by 2
+        if (nbytes > 0) {
+          const float* sp_ = src + (size_t)r0 * p.F_max + g;
+          float* dp_ = dst + r0 * TS + c2;
+          const size_t sstep = (size_t)RPP * p.F_max;
+          const int dstep = RPP * TS;
+          for (int r = r0; r < T; r += RPP) {
+            uint32_t sa = (uint32_t)__cvta_generic_to_shared(dp_);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(sp_), "r"(nbytes));
+            sp_ += sstep;
+            dp_ += dstep;
+          }
+        }
+      }
+    } else {
+      const int total = T * TC;
+      for (int idx = tid; idx < total; idx += nthr) {
+        int r = idx / TC, lc = idx - r * TC;
+        const int g = ts + lc;
+        if (g >= 0 && g < Fp) cp_async4(dst + r * TS + lc, src + (size_t)r * p.F_max + g);
+      }
     }
     cp_async_commit();
   };
@@ -131,7 +161,7 @@ __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
   const int q = tid & 1;
   const int t = tid >> 1;
   const bool row_active = (t < T);
-  const bool interior = (ts >= 0) && (ts + TC <= Fp);  // no reflection, every tile column loaded
+  const bool interior = (f0 - P >= 0) && (f0 + kFT + P <= Fp);  // no reflection, every window column exists
 
   // tile-local column of window element m for this thread (reflect padding, :57)
   auto lc_of = [&](int m) -> int {
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
       const float* rowp = cur + t * TS;
       float v[NV];
       if (!special && interior) {
-        const int cb = kColsPerThr * q;
+        const int cb = kColsPerThr * q + (PA - P);
 #pragma unroll
         for (int m = 0; m < NV; ++m) {
           const int lc = cb + m;
@@ -403,8 +433,9 @@ size_t align_workspace_bytes(int N, int T_max, int F_max) {
 
 template <int P>
 static int launch_reduce(const ReduceParams& rp, int N, int T_max, cudaStream_t st) {
-  constexpr int TC = kFT + 2 * P;
-  constexpr int TS = TC | 1;
+  constexpr int PA = (P + 1) & ~1;
+  constexpr int TC = kFT + 2 * PA;
+  constexpr int TS = TC + 2;
   int T_pad = (T_max + 15) & ~15;
   size_t smem = ((size_t)(2 * T_pad * TS + 28 * TC) * 4 + 7) & ~(size_t)7;
   int threads = 2 * T_pad;
