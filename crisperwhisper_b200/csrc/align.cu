@@ -23,6 +23,7 @@ namespace cw {
 
 static constexpr int kFT = 32;        // output frames per CTA tile
 static constexpr int kColsPerThr = 16;
+static constexpr int kDtwLanes = 128;  // threads (row blocks) per utterance in the DTW kernel
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -70,7 +71,7 @@ struct ReduceParams {
   const float* align;   // [N, H, T_max, F_max]
   const int* T_len;
   const int* F_len;
-  float* cost_t;        // [N, F_max, 32, RP]
+  float* cost_t;        // [N, F_max, 128, RP]
   int H, T_max, F_max, R, RP, tiles_per_utt;
 };
 
@@ -304,43 +305,49 @@ __global__ void __launch_bounds__(896, 1) align_reduce_kernel(ReduceParams p) {
       if (f < Fp) {
         float total = __fadd_rn(acc0[k], acc1s[k * nthr + tid]);
         float m = __fdiv_rn(total, Hf);
-        p.cost_t[(((size_t)n * p.F_max + f) * 32 + lane_blk) * p.RP + rr] = -m;
+        p.cost_t[(((size_t)n * p.F_max + f) * kDtwLanes + lane_blk) * p.RP + rr] = -m;
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// DTW: one CTA of kDtwLanes = 128 threads per utterance. Thread l owns rows [l*R, l*R+R) and processes column j at step
+// s = j + l (skewed wavefront: all 128 row blocks of an anti-diagonal band advance together). Neighbouring row blocks
+// exchange one float per step: by shuffle inside a warp, through a double-buffered shared-memory slot across warps
+// (one __syncthreads per step). Costs live in registers; 2-bit trace codes are packed one word per (step, thread).
 template <int R>
-__global__ void __launch_bounds__(32) dtw_kernel(const float* __restrict__ cost_t, const int* __restrict__ T_len,
-                                                 const int* __restrict__ F_len, int T_max, int F_max,
-                                                 uint32_t* __restrict__ trace, int32_t* __restrict__ jump_out) {
+__global__ void __launch_bounds__(kDtwLanes) dtw_kernel(const float* __restrict__ cost_t, const int* __restrict__ T_len,
+                                                        const int* __restrict__ F_len, int T_max, int F_max,
+                                                        uint32_t* __restrict__ trace, int32_t* __restrict__ jump_out) {
   constexpr int RP = (R + 1) & ~1;
+  constexpr int NL = kDtwLanes;
   const unsigned FULL = 0xffffffffu;
+  __shared__ float s_edge[2][4];  // bottom value of the last lane of each warp, double-buffered by step parity
   const int n = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = T_len[n];
   const int F = F_len[n];
   int32_t* jump = jump_out + (size_t)n * T_max;
-  for (int i = lane; i < T_max; i += 32) jump[i] = 0;
+  for (int i = tid; i < T_max; i += NL) jump[i] = 0;
   if (T <= 0 || F <= 0) return;
-  __syncwarp();
-  const float* cst = cost_t + (size_t)n * F_max * 32 * RP;
-  uint32_t* tr = trace + (size_t)n * (F_max + 32) * 32;
+  const float* cst = cost_t + (size_t)n * F_max * NL * RP;
+  uint32_t* tr = trace + (size_t)n * (F_max + NL) * NL;
   const float INF = __int_as_float(0x7f800000);
+  if (tid < 8) s_edge[tid >> 2][tid & 3] = INF;
+  __syncthreads();
 
-  const int row0 = lane * R;
+  const int row0 = tid * R;
   const int nrows = min(max(T - row0, 0), R);
   float left[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) left[r] = INF;  // cost[i, 0] = inf
   float bottom = INF;
   float diag_in = INF;
-
   float xn[RP];
   auto load_x = [&](int j, float* x) {
     if (j >= 1 && j <= F && nrows > 0) {
-      const float2* src = reinterpret_cast<const float2*>(cst + ((size_t)(j - 1) * 32 + lane) * RP);
+      const float2* src = reinterpret_cast<const float2*>(cst + ((size_t)(j - 1) * NL + tid) * RP);
 #pragma unroll
       for (int k = 0; k < RP / 2; ++k) {
         float2 t2 = __ldg(src + k);
@@ -348,17 +355,18 @@ __global__ void __launch_bounds__(32) dtw_kernel(const float* __restrict__ cost_
       }
     }
   };
-  load_x(1 - lane, xn);
-  const int n_steps = F + 31;
+  load_x(1 - tid, xn);
+  const int n_steps = F + NL - 1;
   for (int s = 1; s <= n_steps; ++s) {
-    const int j = s - lane;
+    const int j = s - tid;
     float x[RP];
 #pragma unroll
     for (int k = 0; k < RP; ++k) x[k] = xn[k];
     load_x(j + 1, xn);
+    // value of the row block above after its previous step (= its bottom row at column j)
     float up_in = __shfl_up_sync(FULL, bottom, 1);
-    if (lane == 0) up_in = INF;  // cost[0, j>=1] = inf
-    float dg = (lane == 0) ? ((j == 1) ? 0.f : INF) : diag_in;
+    if (lane == 0) up_in = (warp == 0) ? INF : s_edge[(s - 1) & 1][warp - 1];
+    float dg = (tid == 0) ? ((j == 1) ? 0.f : INF) : diag_in;
     if (j >= 1 && j <= F && nrows > 0) {
       float up = up_in;
       uint32_t word = 0;
@@ -378,14 +386,17 @@ __global__ void __launch_bounds__(32) dtw_kernel(const float* __restrict__ cost_
         }
       }
       bottom = up;
-      tr[(size_t)s * 32 + lane] = word;
+      tr[(size_t)s * NL + tid] = word;
     }
     diag_in = up_in;
+    if (lane == 31) s_edge[s & 1][warp] = bottom;
+    __syncthreads();
   }
-  __syncwarp();
   __threadfence_block();
+  __syncthreads();
+  if (warp != 0) return;
 
-  // ---- backtrace (:91-115), warp-cooperative: 32 columns of the current lane-block per reload ----------
+  // ---- backtrace (:91-115) by warp 0: 32 columns of the current row block per reload ----------------------------
   int i = T, j = F;
   while (i > 0) {
     if (j == 0) {  // trace[:, 0] = 1: straight up, time index -1
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(32) dtw_kernel(const float* __restrict__ cost_
     const int l = (i - 1) / R;
     const int jc = j - lane;
     uint32_t w = 0;
-    if (jc >= 1) w = tr[(size_t)(jc + l) * 32 + l];
+    if (jc >= 1) w = tr[(size_t)(jc + l) * NL + l];
     const int base_j = j;
     while (i > 0 && j > 0) {
       const int k = base_j - j;
@@ -416,18 +427,16 @@ __global__ void __launch_bounds__(32) dtw_kernel(const float* __restrict__ cost_
 }
 
 static int pick_R(int T_max) {
-  static const int opts[] = {1, 2, 3, 4, 6, 8, 10, 12, 14};
-  int need = (T_max + 31) / 32;
-  for (int o : opts) if (o >= need) return o;
-  return -1;
+  int need = (T_max + kDtwLanes - 1) / kDtwLanes;  // rows per DTW thread
+  return (need >= 1 && need <= 4) ? need : -1;
 }
 
 size_t align_workspace_bytes(int N, int T_max, int F_max) {
   int R = pick_R(T_max);
   if (R < 0) return 0;
   int RP = (R + 1) & ~1;
-  size_t cost = align_up((size_t)N * F_max * 32 * RP * sizeof(float), 256);
-  size_t trace = align_up((size_t)N * (F_max + 32) * 32 * sizeof(uint32_t), 256);
+  size_t cost = align_up((size_t)N * F_max * kDtwLanes * RP * sizeof(float), 256);
+  size_t trace = align_up((size_t)N * (F_max + kDtwLanes) * kDtwLanes * sizeof(uint32_t), 256);
   return cost + trace + 512;
 }
 
@@ -460,8 +469,8 @@ int align_run(cw_ctx* ctx, const float* align, const int32_t* T_len, const int32
   const int R = pick_R(T_max);
   const int RP = (R + 1) & ~1;
   Arena a(ws, ws_bytes);
-  float* cost_t = (float*)a.take((size_t)N * F_max * 32 * RP * sizeof(float));
-  uint32_t* trace = (uint32_t*)a.take((size_t)N * (F_max + 32) * 32 * sizeof(uint32_t));
+  float* cost_t = (float*)a.take((size_t)N * F_max * kDtwLanes * RP * sizeof(float));
+  uint32_t* trace = (uint32_t*)a.take((size_t)N * (F_max + kDtwLanes) * kDtwLanes * sizeof(uint32_t));
 
   ReduceParams rp;
   rp.align = align; rp.T_len = T_len; rp.F_len = F_len; rp.cost_t = cost_t;
@@ -481,10 +490,9 @@ int align_run(cw_ctx* ctx, const float* align, const int32_t* T_len, const int32
   if (rc != CW_OK) return rc;
   if (ctx) ctx->launches += 1;
 #define CW_DTW_CASE(RR) \
-  case RR: dtw_kernel<RR><<<N, 32, 0, st>>>(cost_t, T_len, F_len, T_max, F_max, trace, jump_out); break;
+  case RR: dtw_kernel<RR><<<N, kDtwLanes, 0, st>>>(cost_t, T_len, F_len, T_max, F_max, trace, jump_out); break;
   switch (R) {
-    CW_DTW_CASE(1) CW_DTW_CASE(2) CW_DTW_CASE(3) CW_DTW_CASE(4) CW_DTW_CASE(6) CW_DTW_CASE(8) CW_DTW_CASE(10)
-    CW_DTW_CASE(12) CW_DTW_CASE(14)
+    CW_DTW_CASE(1) CW_DTW_CASE(2) CW_DTW_CASE(3) CW_DTW_CASE(4)
     default: CW_REQUIRE(false, CW_ERR_UNSUPPORTED, "cw_align: R=%d", R);
   }
 #undef CW_DTW_CASE
