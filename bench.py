@@ -359,7 +359,9 @@ def main():
     achieved = step_bytes / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (one launch = one decode step of the whole batch)",
                 "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
-                "traffic": None, "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch, ncu --set full
+                # (profiles/r01_ncu_summary.md: 3.574 GB read + 11 MB written)
+                "traffic": 3585000000, "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
                 "algorithmic_bytes_per_launch": int(step_bytes), "avg_launch_ms": round(per_launch_ms, 4),
                 "launches_timed": n_launch * 3,
                 "bytes_breakdown_GB": {"decoder_weights": round(w_bytes / 1e9, 3), "cross_kv": round(xkv_bytes / 1e9, 3),

@@ -533,47 +533,88 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, const int b, 
   int ts_last_excl = -1;  // scores[ts_begin : ts_last_excl] = -inf
   if (last_ts >= 0) ts_last_excl = (last_was_ts && !penult_was_ts) ? last_ts : last_ts + 1;
 
+  // Every pass below walks the row in batches of 8 independent loads per thread (the row lives in L2: a plain
+  // load-store loop would serialise on ~600-cycle latencies).
+  constexpr int SB = 8;
+  const int bd = blockDim.x;
   // pass 1: masks
   float lmax = NEG;
-  for (int i = tid; i < p.Vp; i += blockDim.x) {
-    float v = lg[i];
-    const uint8_t m = p.suppress[i];
-    bool kill = (m & 4) || (m & 1) || (at_begin && (m & 2));
-    if ((p.flags & CW_DEC_SUPPRESS_EOS) && i == p.eos) kill = true;
-    if (ts_rules) {
-      if (i == p.no_ts) kill = true;
-      if (last_was_ts) {
-        if (penult_was_ts) { if (i >= ts_begin) kill = true; }
-        else { if (i < p.eos) kill = true; }
-      }
-      if (ts_last_excl >= 0 && i >= ts_begin && i < ts_last_excl) kill = true;
-      if (at_begin) {
-        if (i < ts_begin) kill = true;
-        if (p.max_initial_ts >= 0 && i > ts_begin + p.max_initial_ts) kill = true;
-      }
+  for (int i0 = tid; i0 < p.Vp; i0 += SB * bd) {
+    float v8[SB];
+    uint8_t m8[SB];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int i = i0 + u * bd;
+      v8[u] = (i < p.Vp) ? __ldcg(lg + i) : NEG;
+      m8[u] = (i < p.Vp) ? __ldg(p.suppress + i) : (uint8_t)4;
     }
-    if (kill) v = NEG;
-    lg[i] = v;
-    if (i < p.V) lmax = fmaxf(lmax, v);
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int i = i0 + u * bd;
+      if (i >= p.Vp) continue;
+      float v = v8[u];
+      const uint8_t m = m8[u];
+      bool kill = (m & 4) || (m & 1) || (at_begin && (m & 2));
+      if ((p.flags & CW_DEC_SUPPRESS_EOS) && i == p.eos) kill = true;
+      if (ts_rules) {
+        if (i == p.no_ts) kill = true;
+        if (last_was_ts) {
+          if (penult_was_ts) { if (i >= ts_begin) kill = true; }
+          else { if (i < p.eos) kill = true; }
+        }
+        if (ts_last_excl >= 0 && i >= ts_begin && i < ts_last_excl) kill = true;
+        if (at_begin) {
+          if (i < ts_begin) kill = true;
+          if (p.max_initial_ts >= 0 && i > ts_begin + p.max_initial_ts) kill = true;
+        }
+      }
+      if (kill) v = NEG;
+      lg[i] = v;
+      if (i < p.V) lmax = fmaxf(lmax, v);
+    }
   }
   __syncthreads();
   if (ts_rules) {
     // fp32 log_softmax, then logsumexp(timestamps) vs max(text) (:2036-2041)
     const float M = block_reduce_max(lmax, sh);
     float lsum = 0.f;
-    for (int i = tid; i < p.V; i += blockDim.x) lsum += expf(lg[i] - M);
+    for (int i0 = tid; i0 < p.V; i0 += SB * bd) {
+      float v8[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) { const int i = i0 + u * bd; v8[u] = (i < p.V) ? lg[i] : NEG; }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) lsum += expf(v8[u] - M);
+    }
     const float Z = block_reduce_sum(lsum, sh);
     const float lse = M + logf(Z);
     float tmax = NEG, xmax = NEG;
-    for (int i = tid; i < p.V; i += blockDim.x) {
-      float lp = lg[i] - lse;
-      if (i >= ts_begin) tmax = fmaxf(tmax, lp); else xmax = fmaxf(xmax, lp);
+    for (int i0 = tid; i0 < p.V; i0 += SB * bd) {
+      float v8[SB];
+#pragma unroll
+      for (int u = 0; u < SB; ++u) { const int i = i0 + u * bd; v8[u] = (i < p.V) ? lg[i] : NEG; }
+#pragma unroll
+      for (int u = 0; u < SB; ++u) {
+        const int i = i0 + u * bd;
+        if (i < p.V) {
+          const float lp = v8[u] - lse;
+          if (i >= ts_begin) tmax = fmaxf(tmax, lp); else xmax = fmaxf(xmax, lp);
+        }
+      }
     }
     const float TM = block_reduce_max(tmax, sh);
     const float XM = block_reduce_max(xmax, sh);
     float tsum = 0.f;
     if (TM > NEG) {
-      for (int i = ts_begin + tid; i < p.V; i += blockDim.x) tsum += expf((lg[i] - lse) - TM);
+      for (int i0 = ts_begin + tid; i0 < p.V; i0 += SB * bd) {
+        float v8[SB];
+#pragma unroll
+        for (int u = 0; u < SB; ++u) { const int i = i0 + u * bd; v8[u] = (i < p.V) ? lg[i] : NEG; }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+          const int i = i0 + u * bd;
+          if (i < p.V) tsum += expf((v8[u] - lse) - TM);
+        }
+      }
     }
     const float TS = block_reduce_sum(tsum, sh);
     const float ts_logprob = (TM > NEG) ? (logf(TS) + TM) : NEG;
@@ -582,11 +623,22 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, const int b, 
     }
     __syncthreads();
   }
-  // argmax (lowest index among maxima)
+  // argmax (lowest index among maxima); the processed row is copied out in the same sweep when requested
   float bv = NEG; int bi = 0x7fffffff;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    float v = lg[i];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  float* lout = p.logits_out ? p.logits_out + ((size_t)b * p.max_new + step) * p.V : nullptr;
+  for (int i0 = tid; i0 < p.V; i0 += SB * bd) {
+    float v8[SB];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) { const int i = i0 + u * bd; v8[u] = (i < p.V) ? lg[i] : NEG; }
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int i = i0 + u * bd;
+      if (i < p.V) {
+        const float v = v8[u];
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        if (lout) lout[i] = v;
+      }
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -596,10 +648,6 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, const int b, 
   __syncthreads();
   if ((tid & 31) == 0) { sh_v[tid >> 5] = bv; sh_i[tid >> 5] = bi; }
   __syncthreads();
-  if (p.logits_out) {
-    float* dst = p.logits_out + ((size_t)b * p.max_new + step) * p.V;
-    for (int i = tid; i < p.V; i += blockDim.x) dst[i] = lg[i];
-  }
   if (tid == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
       if (sh_v[w] > bv || (sh_v[w] == bv && sh_i[w] < bi)) { bv = sh_v[w]; bi = sh_i[w]; }
