@@ -955,6 +955,17 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
   p.prog = (const PhaseDesc*)bf.prog;
   p.n_phases = (int)prog.size();
   p.prefetch = mega_prefetch_enabled() ? 1 : 0;
+  {  // L2 prefetch distance (phases) and per-phase byte cap; CW_MEGA_L2PF=0 turns it off, CW_MEGA_L2PF_MB sets the cap
+    const char* e = getenv("CW_MEGA_L2PF");
+    p.l2pf = e ? atoi(e) : 0;
+    if (p.l2pf < 0) p.l2pf = 0;
+    if (p.l2pf > 4) p.l2pf = 4;
+    const char* c = getenv("CW_MEGA_L2PF_MB");
+    int mb = c ? atoi(c) : 64;
+    if (mb < 1) mb = 1;
+    if (mb > 1024) mb = 1024;
+    p.l2pf_cap = (unsigned int)mb << 20;
+  }
   CW_CUDA(cudaMemcpyToSymbolAsync(c_mp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
   CW_CUDA(cudaStreamSynchronize(st));  // `p` is a stack object
   return CW_OK;
@@ -967,6 +978,7 @@ static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
   const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4 +
                       (mega_prefetch_enabled() ? (size_t)kMegaWarps * 5 * 64 * 16 : 0);
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
+  CW_REQUIRE(m.ffn_dim >= 2 * m.d_model, CW_ERR_UNSUPPORTED, "decode megakernel: ffn_dim %d < 2 * d_model", m.ffn_dim);
   CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -49,6 +49,8 @@ struct MegaParams {
   unsigned int* bar;         // grid barrier counter
   unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
   const struct PhaseDesc* prog; int n_phases; int prefetch;   // the step as a list of phases (built on the host once per call)
+  int l2pf;                  // L2 prefetch distance in phases (0 = off)
+  unsigned int l2pf_cap;     // at most this many bytes of one phase's operand are prefetched
   SampleParams sp;
 };
 
@@ -57,13 +59,15 @@ __device__ __forceinline__ float4 ld_cg4(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ uint4 ld_cg16(const uint4* p) { return __ldcg(p); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel). Bounded spin -> trap.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+// Grid-wide barrier on a monotonically increasing counter (zeroed by dec_init_kernel). Every launch passes exactly
+// n_phases barriers, so the value that completes barrier `ph` of the step at position `pos` is known up front: the
+// arrival is a fire-and-forget red.release (no round trip for the old value) and the poll starts right behind it.
+// __syncthreads + release by one thread / acquire by one thread + __syncthreads orders the whole CTA's global writes
+// before, and its reads after, the barrier (release/acquire are cumulative over the bar.sync). Bounded spin -> trap.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(bar, 1u);
-    const unsigned int target = (old / nblocks + 1u) * nblocks;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int spins = 0;
     while (true) {
       unsigned int v;
@@ -71,16 +75,26 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
       if ((int)(v - target) >= 0) break;
       if (++spins > (1u << 26)) __trap();
     }
-    __threadfence();
   }
   __syncthreads();
 }
 
 // ---- activation staging: rows of B samples -> bf16 [8][K+32] in smem --------------------------------------
-__device__ __forceinline__ void stage_ln(bf16* xs, int XS, const float* x, const float* g, const float* bt, int K, int B) {
+// LayerNorm of the B rows into xs (bf16). Warps 0..7 own one row each (values stay in registers between the statistics
+// and the normalisation); meanwhile warps 8..15 fetch gamma/beta into smem and signal named barrier 15 (arrive only),
+// so that round trip is off the rows' chain. Ends with a CTA-wide barrier: on return xs is complete.
+__device__ __forceinline__ void stage_ln(bf16* xs, int XS, float* gb /* smem [2][K] */, const float* x, const float* g,
+                                         const float* bt, int K, int B) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = K >> 7;
-  if (warp < 8) {
+  if (warp >= 8) {
+    const int i0 = threadIdx.x - 256, n4 = K >> 2;
+    for (int i = i0; i < 2 * n4; i += 256) {
+      const float4 w = (i < n4) ? __ldg(reinterpret_cast<const float4*>(g) + i) : __ldg(reinterpret_cast<const float4*>(bt) + (i - n4));
+      reinterpret_cast<float4*>(gb)[i] = w;
+    }
+    asm volatile("bar.arrive 15, %0;" ::"r"(kMegaThreads) : "memory");
+  } else {
     bf16* dst = xs + (size_t)warp * XS;
     if (warp < B) {
       const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * K);
@@ -102,12 +116,13 @@ __device__ __forceinline__ void stage_ln(bf16* xs, int XS, const float* x, const
       }
       for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
       const float rstd = rsqrtf(q / (float)K + 1e-5f);
-      const float4* g4 = reinterpret_cast<const float4*>(g);
-      const float4* b4 = reinterpret_cast<const float4*>(bt);
+      asm volatile("bar.sync 15, %0;" ::"r"(kMegaThreads) : "memory");
+      const float4* g4 = reinterpret_cast<const float4*>(gb);
+      const float4* b4 = reinterpret_cast<const float4*>(gb + K);
 #pragma unroll
       for (int i = 0; i < 10; ++i) {
         if (i < nv) {
-          const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+          const float4 gg = g4[lane + 32 * i], bb = b4[lane + 32 * i];
           __nv_bfloat162 h0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
           __nv_bfloat162 h1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
           uint2 u;
@@ -118,8 +133,10 @@ __device__ __forceinline__ void stage_ln(bf16* xs, int XS, const float* x, const
       }
     } else {
       for (int k = lane; k < K; k += 32) dst[k] = __float2bfloat16(0.f);
+      asm volatile("bar.sync 15, %0;" ::"r"(kMegaThreads) : "memory");
     }
   }
+  __syncthreads();
 }
 
 __device__ __forceinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
@@ -405,13 +422,51 @@ __device__ __forceinline__ bool gemv_prefetch(const PhaseDesc* D) {
   return true;
 }
 
+// ---- L2 prefetch of a later phase's read-only operand ---------------------------------------------------------
+// The phases are short and dependent, so HBM idles during every barrier and latency chain. Weights, the cross K/V of a
+// layer and the self-attention cache rows of earlier positions do not depend on this step's activations: each CTA asks
+// the TMA unit (cp.async.bulk.prefetch.L2 — no registers, no smem, nothing to wait on) to pull its share of the operand
+// of phase ph+dist into L2 while phase ph runs, so the demand loads of that phase hit L2 instead of HBM.
+// One lane per warp issues (the instruction takes warp-uniform operands); chunk c of the span goes to warp c mod #warps.
+__device__ __forceinline__ void l2_prefetch_chunks(const char* p, size_t bytes, int first, int stride) {
+  constexpr unsigned CH = 16384;
+  if ((threadIdx.x & 31) != 0) return;
+  const size_t n_chunks = (bytes + CH - 1) / CH;
+  for (size_t c = first; c < n_chunks; c += stride) {
+    const size_t off = c * CH;
+    const unsigned sz = (unsigned)min((size_t)CH, bytes - off) & ~15u;
+    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz) : "memory");
+  }
+}
+__device__ __forceinline__ void l2_prefetch_span(const void* base, size_t bytes) {
+  l2_prefetch_chunks(reinterpret_cast<const char*>(base), bytes, blockIdx.x + gridDim.x * (threadIdx.x >> 5), gridDim.x * kMegaWarps);
+}
+
+__device__ __forceinline__ void l2_prefetch_phase(const PhaseDesc* D, int pos) {
+  const size_t cap = c_mp.l2pf_cap;
+  const int type = D->type;
+  if (type == PH_GEMV) {
+    l2_prefetch_span(D->W, min((size_t)D->N * D->K * sizeof(bf16), cap));
+  } else if (type == PH_CROSS_ATTN) {
+    const size_t xkv_l = (size_t)c_mp.B * c_mp.F * 2 * c_mp.d;
+    l2_prefetch_span(c_mp.xkv + D->l * xkv_l, min(xkv_l * sizeof(bf16), cap));
+  } else if (type == PH_SELF_ATTN) {
+    // rows [0, pos) of every sample's K and V cache (row `pos` is written by the preceding projection phase)
+    const size_t cache_l = (size_t)c_mp.B * c_mp.n_ctx * c_mp.d;
+    const size_t row_bytes = (size_t)pos * c_mp.d * sizeof(bf16);
+    const int spans = 2 * c_mp.B;
+    const int span = blockIdx.x % spans, part = blockIdx.x / spans, parts = (gridDim.x + spans - 1) / spans;
+    const bf16* cache = (span & 1) ? c_mp.vc : c_mp.kc;
+    const char* base = reinterpret_cast<const char*>(cache + D->l * cache_l + (size_t)(span >> 1) * c_mp.n_ctx * c_mp.d);
+    l2_prefetch_chunks(base, row_bytes, part + parts * (threadIdx.x >> 5), parts * kMegaWarps);
+  }
+}
+
 __device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos, bool have_pre) {
   const int N = D->N, K = D->K, XS = K + 32;
   const bool ln = D->ln != 0;
-  if (ln) {
-    stage_ln(sm_xs(), XS, D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
-    __syncthreads();
-  }
+  if (ln)  // gamma/beta staging sits behind the K-wide xs rows (the region is sized for ffn >= 2 K)
+    stage_ln(sm_xs(), XS, reinterpret_cast<float*>(msm + (size_t)8 * XS * sizeof(bf16)), D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
   GemvOut o;
   o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
   o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
@@ -510,11 +565,17 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
   unsigned long long t_prev = 0;
   mega_tick(-1, t_prev);
   const int n_ph = c_mp.n_phases;
+  const int pf = c_mp.l2pf;
   bool have_pre = false;
 #pragma unroll 1
   for (int ph = 0; ph < n_ph; ++ph) {
     const PhaseDesc* D = c_mp.prog + ph;
     const int type = D->type;
+    if (pf > 0) {  // operand of phase ph+pf -> L2; past the end of the program: the first phases of the next step
+      const int q = ph + pf;
+      if (q < n_ph) l2_prefetch_phase(c_mp.prog + q, pos);
+      else l2_prefetch_phase(c_mp.prog + (q - n_ph), pos + 1);
+    }
     if (type == PH_GEMV) ph_gemv(D, pos, have_pre);
     else if (type == PH_CROSS_ATTN) ph_cross_attn(D->l, pos, s_flag);
     else if (type == PH_SELF_ATTN) ph_self_attn(D->l, pos);
@@ -523,7 +584,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
     if (c_mp.prefetch && ph + 1 < n_ph && D[1].type == PH_GEMV) have_pre = gemv_prefetch(D + 1);
     const int slot = D->dbg_slot;
     mega_tick(2 * slot, t_prev);
-    grid_barrier(c_mp.bar, gridDim.x);
+    grid_barrier(c_mp.bar, ((unsigned int)pos * (unsigned int)n_ph + (unsigned int)ph + 1u) * gridDim.x);
     mega_tick(2 * slot + 1, t_prev);
   }
   if ((int)blockIdx.x < c_mp.B) sample_body(c_mp.sp, blockIdx.x, pos, sh, sh_i, sh_v);
