@@ -888,13 +888,11 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   return CW_OK;
 }
 
-// Cross-barrier weight prefetch (cp.async into per-lane smem slots) is implemented but OFF by default: measured on B200
-// it costs more than it hides (2.83 vs 2.44 ms/step) — 20 LDGSTS per thread are ~1.3 us of issue time per phase, and
-// the 80 KB buffer shrinks L1. CW_MEGA_PREFETCH=1 enables it for experiments.
-static bool mega_prefetch_enabled() {
-  const char* e = getenv("CW_MEGA_PREFETCH");
-  return e != nullptr && e[0] == '1';
-}
+// Measured and rejected on B200 (each was slower than the plain kernel): carrying the first weight batch of
+// the next projection across the grid barrier in registers or in a cp.async smem buffer (2.83 vs 2.44 ms/step), pulling
+// the next phase's operand into L2 with cp.async.bulk.prefetch.L2 (2.69 vs 2.39 ms/step), and issuing a phase's first
+// weight batch before its LayerNorm (2.29 vs 2.26 ms/step). ncu: the warps wait on barriers and dependent loads (stall
+// barrier 11.4, long scoreboard 5.1 per issued instruction); HBM bandwidth and instruction fetch are not the limiters.
 
 // fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
 static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
@@ -954,18 +952,6 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
   CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice, st));
   p.prog = (const PhaseDesc*)bf.prog;
   p.n_phases = (int)prog.size();
-  p.prefetch = mega_prefetch_enabled() ? 1 : 0;
-  {  // L2 prefetch distance (phases) and per-phase byte cap; CW_MEGA_L2PF=0 turns it off, CW_MEGA_L2PF_MB sets the cap
-    const char* e = getenv("CW_MEGA_L2PF");
-    p.l2pf = e ? atoi(e) : 0;
-    if (p.l2pf < 0) p.l2pf = 0;
-    if (p.l2pf > 4) p.l2pf = 4;
-    const char* c = getenv("CW_MEGA_L2PF_MB");
-    int mb = c ? atoi(c) : 64;
-    if (mb < 1) mb = 1;
-    if (mb > 1024) mb = 1024;
-    p.l2pf_cap = (unsigned int)mb << 20;
-  }
   CW_CUDA(cudaMemcpyToSymbolAsync(c_mp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
   CW_CUDA(cudaStreamSynchronize(st));  // `p` is a stack object
   return CW_OK;
@@ -974,11 +960,12 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
 // one cooperative launch for the whole step
 static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
   const ModelDesc& m = ctx->md;
-  const int kmax = m.ffn_dim > m.d_model ? m.ffn_dim : m.d_model;
-  const size_t smem = (size_t)8 * (kmax + 32) * 2 + (size_t)kMegaWarps * 128 * 4 +
-                      (mega_prefetch_enabled() ? (size_t)kMegaWarps * 5 * 64 * 16 : 0);
+  const size_t smem_gemv = (size_t)8 * (m.d_model + 32) * 2 + (size_t)2 * m.d_model * 4 + (size_t)kMegaWarps * 128 * 4;
+  // attention phases alias the same buffer: 4 groups x 8 KB scratch + the cross-attention K/V rings
+  const size_t smem_attn = (size_t)4 * 2048 * 4 + (size_t)4 * kXRing * 2 * 128 * 16;
+  const size_t smem = smem_gemv > smem_attn ? smem_gemv : smem_attn;
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
-  CW_REQUIRE(m.ffn_dim >= 2 * m.d_model, CW_ERR_UNSUPPORTED, "decode megakernel: ffn_dim %d < 2 * d_model", m.ffn_dim);
+  CW_REQUIRE(m.n_text_ctx <= 1024 && m.n_audio_ctx <= kXSplit * 512, CW_ERR_UNSUPPORTED, "decode megakernel: context too long");
   CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -48,9 +48,7 @@ struct MegaParams {
   unsigned int* xcount;      // [B*H]
   unsigned int* bar;         // grid barrier counter
   unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
-  const struct PhaseDesc* prog; int n_phases; int prefetch;   // the step as a list of phases (built on the host once per call)
-  int l2pf;                  // L2 prefetch distance in phases (0 = off)
-  unsigned int l2pf_cap;     // at most this many bytes of one phase's operand are prefetched
+  const struct PhaseDesc* prog; int n_phases;   // the step as a list of phases (built on the host once per call)
   SampleParams sp;
 };
 
@@ -139,31 +137,6 @@ __device__ __forceinline__ void stage_ln(bf16* xs, int XS, float* gb /* smem [2]
   __syncthreads();
 }
 
-__device__ __forceinline__ void stage_bf16(bf16* xs, int XS, const bf16* src, int K, int B) {
-  const int vec_per_row = K >> 3;
-  const int total = 8 * vec_per_row;
-  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kMegaThreads) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kMegaThreads;
-      v[u] = make_uint4(0, 0, 0, 0);
-      if (i < total) {
-        const int b = i / vec_per_row, c = i - b * vec_per_row;
-        if (b < B) v[u] = ld_cg16(reinterpret_cast<const uint4*>(src + (size_t)b * K + c * 8));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * kMegaThreads;
-      if (i < total) {
-        const int b = i / vec_per_row, c = i - b * vec_per_row;
-        *reinterpret_cast<uint4*>(xs + (size_t)b * XS + c * 8) = v[u];
-      }
-    }
-  }
-}
-
 struct GemvOut {
   float* out_f32;   // F32 / RESID / QKV(q)
   bf16* out_bf16;   // GELU_BF16
@@ -175,9 +148,7 @@ struct GemvOut {
 // Weight loads of a tile are issued before the activations are staged.  xs must already be staged unless `stage` is set.
 __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const float* __restrict__ bias, int N, int K, int B,
                                           const bf16* xs, int XS, float* red, const GemvOut o, const int KW, const int epi,
-                                          const bf16* __restrict__ direct /* bf16 [B, K] activations read straight from L2, or null */,
-                                          const bool have_pre /* first batch of the first tile is already in smem */,
-                                          const uint4* pre_base) {
+                                          const bf16* __restrict__ direct /* bf16 [B, K] activations read straight from L2, or null */) {
   const int S = kMegaWarps / KW;        // concurrent tiles per CTA
   const int GT = KW * 32;               // threads per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,18 +170,11 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
     constexpr int U = 5;
     for (int c0 = 0; c0 < chunks; c0 += U) {
       uint4 a0[U], a1[U], xd[U];
-      const bool from_smem = have_pre && c0 == 0 && tile == (int)(blockIdx.x + gridDim.x * grp);
-      const uint4* pb = pre_base + (size_t)warp * (U * 64) + lane;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (c0 + u < chunks) {
-          if (from_smem) {
-            a0[u] = pb[u * 64];
-            a1[u] = pb[u * 64 + 32];
-          } else {
-            a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
-            a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
-          }
+          a0[u] = ldg_stream(w0 + (size_t)(c0 + u) * 32);
+          a1[u] = ldg_stream(w1 + (size_t)(c0 + u) * 32);
           if (direct != nullptr) {  // B fragment of sample g straight from L2 (no smem staging, no CTA-wide sync)
             xd[u] = make_uint4(0, 0, 0, 0);
             if (g < B) xd[u] = ld_cg16(reinterpret_cast<const uint4*>(direct + (size_t)g * K + kbeg + (c0 + u) * 32 + 8 * t));
@@ -260,122 +224,118 @@ __device__ __forceinline__ void mega_gemv(const bf16* __restrict__ W, const floa
   }
 }
 
-// Attention of one query row over n rows by a group of GT threads (8 threads per row). Returns, in smem/regs:
-// sp[j] = exp(score_j - m), local max m and sum l (broadcast to every thread), acc -> so then out[64] in so[0][..].
-template <int GT, int UN>
-__device__ __forceinline__ float2 group_attend(const float* __restrict__ q64, const bf16* __restrict__ kb,
-                                               const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
-                                               float* sq, float* sp, float* sred, float* so /*[GT/8][65]*/) {
+// Single-pass (online softmax) attention of one query row over n rows by a group of GT threads, 8 threads per row, with
+// the K and V rows streamed through a D-deep cp.async ring in smem. Every thread reads back only the 2 x 16 B it fetched
+// itself, so the loop needs no barrier: cp.async.wait_group is the only synchronisation, and D - 1 row sets per thread
+// (GT / 8 rows x 256 B each) stay in flight from before the query is even available until the last row.
+// Each 8-thread sub-group keeps its own running (max, sum, out[64]); they are merged through smem at the end.
+// Scores are kept in the log2 domain (q is pre-multiplied by log2 e), exponentials are single ex2.approx instructions.
+// On return: sp[j] = log2-domain score of row j, so[0..63] = sum_j 2^(sp_j - M) v_j; returns (M, sum_j 2^(sp_j - M)).
+#ifndef CW_XRING
+#define CW_XRING 6
+#endif
+static constexpr int kXRing = CW_XRING;   // ring depth of the cross-attention groups
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int GT, int D>
+__device__ __forceinline__ float2 group_attend_pipe(const float* __restrict__ q64, const bf16* __restrict__ kb,
+                                                    const bf16* __restrict__ vb, size_t row_stride, int n, int gtid, int bar_id,
+                                                    float* sq, float* sp, float* smx /*[GT/8]*/, float* sl /*[GT/8]*/,
+                                                    float* so /*[GT/8][64]*/, uint4* ring /*[D][2][GT]*/) {
   constexpr int G = GT / 8;
   const int sub = gtid & 7, grp = gtid >> 3;
-  // first K batch goes out before the query is fetched: K (cache / encoder rows) does not depend on this step's q
-  uint4 u[UN];
+  const int n_it = (n + G - 1) / G;      // uniform over the group (and so over each of its warps)
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + gtid);
+  const bf16* krow = kb + (size_t)grp * row_stride + sub * 8;
+  const bf16* vrow = vb + (size_t)grp * row_stride + sub * 8;
+  const size_t it_stride = (size_t)G * row_stride;
+  int issue_it = 0, issue_slot = 0;
+  auto issue = [&]() {
+    if (issue_it < n_it && grp + G * issue_it < n) {
+      const uint32_t dst = ring_s + (uint32_t)(issue_slot * 2 * GT * 16);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(krow + issue_it * it_stride) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + GT * 16), "l"(vrow + issue_it * it_stride) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ++issue_it;
+    issue_slot = (issue_slot + 1 == D) ? 0 : issue_slot + 1;
+  };
 #pragma unroll
-  for (int x = 0; x < UN; ++x) {
-    const int j = grp + G * x;
-    u[x] = make_uint4(0, 0, 0, 0);
-    if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
-  }
+  for (int st = 0; st < D - 1; ++st) issue();
   if (gtid < 64) sq[gtid] = ld_cg(q64 + gtid);
   named_bar(bar_id, GT);
   float qv[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e];
-  for (int base = 0; base < n; base += G * UN) {
-    if (base > 0) {
-#pragma unroll
-      for (int x = 0; x < UN; ++x) {
-        const int j = base + grp + G * x;
-        u[x] = make_uint4(0, 0, 0, 0);
-        if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(kb + (size_t)j * row_stride) + sub);
-      }
-    }
-#pragma unroll
-    for (int x = 0; x < UN; ++x) {
-      const int j = base + grp + G * x;
-      float s = (j < n) ? dot8(u[x], qv) : 0.f;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (sub == 0 && j < n) sp[j] = s;
-    }
-  }
-  // first V batch is issued now and lands while the softmax statistics are computed
-#pragma unroll
-  for (int x = 0; x < UN; ++x) {
-    const int j = grp + G * x;
-    u[x] = make_uint4(0, 0, 0, 0);
-    if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
-  }
-  named_bar(bar_id, GT);
-  float lmax = -INFINITY;
-  for (int j = gtid; j < n; j += GT) lmax = fmaxf(lmax, sp[j]);
-  for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  if ((gtid & 31) == 0) sred[gtid >> 5] = lmax;
-  named_bar(bar_id, GT);
-  float mx = sred[0];
-#pragma unroll
-  for (int w = 1; w < GT / 32; ++w) mx = fmaxf(mx, sred[w]);
-  named_bar(bar_id, GT);
-  float lsum = 0.f;
-  for (int j = gtid; j < n; j += GT) { float e = expf(sp[j] - mx); sp[j] = e; lsum += e; }
-  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  if ((gtid & 31) == 0) sred[gtid >> 5] = lsum;
-  named_bar(bar_id, GT);
-  float tot = 0.f;
-#pragma unroll
-  for (int w = 0; w < GT / 32; ++w) tot += sred[w];
+  for (int e = 0; e < 8; ++e) qv[e] = sq[sub * 8 + e] * 1.4426950408889634f;  // scores in the log2 domain: one MUFU.EX2 per row
+  float m = -INFINITY, l = 0.f;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int base = 0; base < n; base += G * UN) {
-    if (base > 0) {
+  int slot = 0;
+  for (int it = 0; it < n_it; ++it) {
+    issue();  // refills the slot consumed in the previous iteration
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(D - 1) : "memory");
+    const int j = grp + G * it;
+    const uint4 ku = ring[(size_t)slot * 2 * GT + gtid];
+    const uint4 vu = ring[(size_t)slot * 2 * GT + GT + gtid];
+    slot = (slot + 1 == D) ? 0 : slot + 1;
+    float s = (j < n) ? dot8(ku, qv) : 0.f;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (j < n) {
+      if (sub == 0) sp[j] = s;
+      if (s > m) {  // new running maximum (rare after the first rows): rescale what has been accumulated
+        const float sc = ex2_approx(m - s);
+        m = s;
+        l *= sc;
 #pragma unroll
-      for (int x = 0; x < UN; ++x) {
-        const int j = base + grp + G * x;
-        u[x] = make_uint4(0, 0, 0, 0);
-        if (j < n) u[x] = ldg_stream(reinterpret_cast<const uint4*>(vb + (size_t)j * row_stride) + sub);
+        for (int e = 0; e < 8; ++e) acc[e] *= sc;
       }
-    }
+      const float pj = ex2_approx(s - m);
+      l += pj;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vu);
 #pragma unroll
-    for (int x = 0; x < UN; ++x) {
-      const int j = base + grp + G * x;
-      if (j < n) {
-        const float pj = sp[j];
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u[x]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 f = __bfloat1622float2(h2[e]);
-          acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
-          acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  if (sub == 0) { smx[grp] = m; sl[grp] = l; }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) so[grp * 65 + sub * 8 + e] = acc[e];
+  for (int e = 0; e < 8; ++e) so[grp * 64 + sub * 8 + e] = acc[e];
   named_bar(bar_id, GT);
+  float M = smx[0];
+#pragma unroll
+  for (int r = 1; r < G; ++r) M = fmaxf(M, smx[r]);
+  float L = 0.f;
+#pragma unroll
+  for (int r = 0; r < G; ++r) L += sl[r] * ex2_approx(smx[r] - M);
   if (gtid < 64) {
     float v = 0.f;
-    for (int r = 0; r < G; ++r) v += so[r * 65 + gtid];
-    so[gtid] = v;  // row 0, column gtid (each thread only overwrites the element it just finished reading in its column)
+    for (int r = 0; r < G; ++r) v += so[r * 64 + gtid] * ex2_approx(smx[r] - M);
+    so[gtid] = v;  // row 0, column gtid: each thread overwrites only the element it has just read in its own column
   }
   named_bar(bar_id, GT);
-  return make_float2(mx, tot);
+  return make_float2(M, L);
 }
 
 // The step parameters live in constant memory (copied once per cw_decode_greedy call).
 __constant__ MegaParams c_mp;
 
 extern __shared__ __align__(16) unsigned char msm[];
-// dynamic smem: xs bf16 [8][ffn+32] | red f32 [16][128]; the attention scratch aliases xs (phases never overlap in a CTA)
+// dynamic smem: xs bf16 [8][d+32] (LayerNorm-ed rows; the other projections read bf16 activations straight from L2) |
+// gamma/beta f32 [2][d] | red f32 [16][128]; the attention scratch and K/V rings alias all of it (phases never overlap)
 __device__ __forceinline__ bf16* sm_xs() { return reinterpret_cast<bf16*>(msm); }
-__device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(msm + (size_t)8 * (c_mp.ffn + 32) * 2); }
+__device__ __forceinline__ float* sm_gb() { return reinterpret_cast<float*>(msm + (size_t)8 * (c_mp.d + 32) * 2); }
+__device__ __forceinline__ float* sm_red() { return sm_gb() + 2 * c_mp.d; }
 __device__ __forceinline__ float* sm_attn() { return reinterpret_cast<float*>(msm); }
-// weight prefetch buffer: [16 warps][5 chunks][2 row halves][32 lanes] x 16 B = 80 KB, every lane owns its slots
-__device__ __forceinline__ uint4* sm_pre() {
-  return reinterpret_cast<uint4*>(msm + (size_t)8 * (c_mp.ffn + 32) * 2 + (size_t)kMegaWarps * 128 * 4);
-}
 
 __device__ __forceinline__ void ph_embed(int pos) {
   const int d = c_mp.d;
@@ -393,86 +353,15 @@ __device__ __forceinline__ int gemv_kw_of(const PhaseDesc* D) {
   return (kmax >= 16 && K % 512 == 0) ? 16 : ((kmax >= 8 && K % 256 == 0) ? 8 : 4);  // widest K-split with 32-multiples
 }
 
-// Start fetching (cp.async, no registers) the first weight batch of this warp's first tile of GEMV phase D into the
-// warp's slots of sm_pre(). Weights never change while decoding, so this is issued before the grid barrier that precedes
-// the phase and lands while the CTA waits / stages activations. Mirrors the index arithmetic of mega_gemv.
-__device__ __forceinline__ bool gemv_prefetch(const PhaseDesc* D) {
-  const int KW = gemv_kw_of(D);
-  const int K = D->K;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp / KW, wl = warp - grp * KW;
-  const int g = lane >> 2, t = lane & 3;
-  const int tile = blockIdx.x + gridDim.x * grp;
-  if (tile >= (D->N >> 4)) return false;
-  const int kslice = K / KW;
-  const int chunks = kslice >> 5;
-  const bf16* w0 = D->W + (size_t)((tile << 4) + g) * K + wl * kslice + 8 * t;
-  const bf16* w1 = w0 + (size_t)8 * K;
-  uint4* pb = sm_pre() + (size_t)warp * (5 * 64) + lane;
-#pragma unroll
-  for (int u = 0; u < 5; ++u) {
-    if (u < chunks) {
-      const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(pb + u * 64);
-      const uint32_t s1 = (uint32_t)__cvta_generic_to_shared(pb + u * 64 + 32);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s0), "l"(w0 + (size_t)u * 32));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s1), "l"(w1 + (size_t)u * 32));
-    }
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-  return true;
-}
-
-// ---- L2 prefetch of a later phase's read-only operand ---------------------------------------------------------
-// The phases are short and dependent, so HBM idles during every barrier and latency chain. Weights, the cross K/V of a
-// layer and the self-attention cache rows of earlier positions do not depend on this step's activations: each CTA asks
-// the TMA unit (cp.async.bulk.prefetch.L2 — no registers, no smem, nothing to wait on) to pull its share of the operand
-// of phase ph+dist into L2 while phase ph runs, so the demand loads of that phase hit L2 instead of HBM.
-// One lane per warp issues (the instruction takes warp-uniform operands); chunk c of the span goes to warp c mod #warps.
-__device__ __forceinline__ void l2_prefetch_chunks(const char* p, size_t bytes, int first, int stride) {
-  constexpr unsigned CH = 16384;
-  if ((threadIdx.x & 31) != 0) return;
-  const size_t n_chunks = (bytes + CH - 1) / CH;
-  for (size_t c = first; c < n_chunks; c += stride) {
-    const size_t off = c * CH;
-    const unsigned sz = (unsigned)min((size_t)CH, bytes - off) & ~15u;
-    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + off), "r"(sz) : "memory");
-  }
-}
-__device__ __forceinline__ void l2_prefetch_span(const void* base, size_t bytes) {
-  l2_prefetch_chunks(reinterpret_cast<const char*>(base), bytes, blockIdx.x + gridDim.x * (threadIdx.x >> 5), gridDim.x * kMegaWarps);
-}
-
-__device__ __forceinline__ void l2_prefetch_phase(const PhaseDesc* D, int pos) {
-  const size_t cap = c_mp.l2pf_cap;
-  const int type = D->type;
-  if (type == PH_GEMV) {
-    l2_prefetch_span(D->W, min((size_t)D->N * D->K * sizeof(bf16), cap));
-  } else if (type == PH_CROSS_ATTN) {
-    const size_t xkv_l = (size_t)c_mp.B * c_mp.F * 2 * c_mp.d;
-    l2_prefetch_span(c_mp.xkv + D->l * xkv_l, min(xkv_l * sizeof(bf16), cap));
-  } else if (type == PH_SELF_ATTN) {
-    // rows [0, pos) of every sample's K and V cache (row `pos` is written by the preceding projection phase)
-    const size_t cache_l = (size_t)c_mp.B * c_mp.n_ctx * c_mp.d;
-    const size_t row_bytes = (size_t)pos * c_mp.d * sizeof(bf16);
-    const int spans = 2 * c_mp.B;
-    const int span = blockIdx.x % spans, part = blockIdx.x / spans, parts = (gridDim.x + spans - 1) / spans;
-    const bf16* cache = (span & 1) ? c_mp.vc : c_mp.kc;
-    const char* base = reinterpret_cast<const char*>(cache + D->l * cache_l + (size_t)(span >> 1) * c_mp.n_ctx * c_mp.d);
-    l2_prefetch_chunks(base, row_bytes, part + parts * (threadIdx.x >> 5), parts * kMegaWarps);
-  }
-}
-
-__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos, bool have_pre) {
+__device__ __forceinline__ void ph_gemv(const PhaseDesc* D, int pos) {
   const int N = D->N, K = D->K, XS = K + 32;
   const bool ln = D->ln != 0;
-  if (ln)  // gamma/beta staging sits behind the K-wide xs rows (the region is sized for ffn >= 2 K)
-    stage_ln(sm_xs(), XS, reinterpret_cast<float*>(msm + (size_t)8 * XS * sizeof(bf16)), D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);
+  if (ln) stage_ln(sm_xs(), XS, sm_gb(), D->src_f32, D->ln_g, D->ln_b, K, c_mp.B);  // LN phases have K == d
   GemvOut o;
   o.out_f32 = D->out_f32; o.out_bf16 = D->out_bf16; o.kcache = D->kcache; o.vcache = D->vcache;
   o.d = c_mp.d; o.n_ctx = c_mp.n_ctx; o.pos = pos;
   const int KW = gemv_kw_of(D);
-  if (have_pre) asm volatile("cp.async.wait_group 0;\n" ::: "memory");  // each lane reads back only its own slots
-  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi, ln ? nullptr : D->src_bf16, have_pre, sm_pre());
+  mega_gemv(D->W, D->bias, N, K, c_mp.B, sm_xs(), XS, sm_red(), o, KW, D->epi, ln ? nullptr : D->src_bf16);
 }
 
 __device__ __forceinline__ void ph_self_attn(int l, int pos) {
@@ -483,12 +372,14 @@ __device__ __forceinline__ void ph_self_attn(int l, int pos) {
   if (task >= c_mp.B * H) return;
   const size_t cache_l = (size_t)c_mp.B * c_mp.n_ctx * d;
   const int b = task / H, h = task - b * H;
-  float* base = sm_attn() + grp * 4096;     // sq[64] | sp[448] | sred[8] | so[32*65]
+  float* base = sm_attn() + grp * 4096;     // sq[64] | sp[n_ctx <= 1024] | max[32] | sum[32] | so[32*64]
+  uint4* ring = reinterpret_cast<uint4*>(sm_attn() + 2 * 4096) + (size_t)grp * (kXRing * 2 * 256);
   const bf16* kc = c_mp.kc + l * cache_l + (size_t)b * c_mp.n_ctx * d + h * 64;
   const bf16* vc = c_mp.vc + l * cache_l + (size_t)b * c_mp.n_ctx * d + h * 64;
-  const float2 ml = group_attend<256, 4>(c_mp.qbuf + (size_t)b * d + h * 64, kc, vc, (size_t)d, pos + 1, gtid, 1 + grp, base,
-                                         base + 64, base + 64 + 448, base + 64 + 448 + 8);
-  if (gtid < 64) c_mp.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(base[64 + 448 + 8 + gtid] / ml.y);
+  float* so = base + 64 + 1024 + 64;
+  const float2 ml = group_attend_pipe<256, kXRing>(c_mp.qbuf + (size_t)b * d + h * 64, kc, vc, (size_t)d, pos + 1, gtid, 1 + grp, base,
+                                                   base + 64, base + 64 + 1024, base + 64 + 1024 + 32, so, ring);
+  if (gtid < 64) c_mp.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(so[gtid] / ml.y);
 }
 
 __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
@@ -497,7 +388,8 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
   const int grp = warp >> 2, gtid = threadIdx.x & 127;
   const int sub_id = blockIdx.x + gridDim.x * grp;
   if (sub_id >= c_mp.B * H * kXSplit) return;
-  float* base = sm_attn() + grp * 2048;     // sq[64] | sp[500] | sred[4] | so[16*65]
+  float* base = sm_attn() + grp * 2048;     // sq[64] | sp[512] | max[16] | sum[16] | so[16*64]
+  uint4* ring = reinterpret_cast<uint4*>(sm_attn() + 4 * 2048) + (size_t)grp * (kXRing * 2 * 128);
   const int task = sub_id / kXSplit, split = sub_id - task * kXSplit;
   const int b = task / H, h = task - b * H;
   const int f0 = split * kXFrames;
@@ -506,16 +398,22 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
   const size_t xkv_l = (size_t)c_mp.B * F * 2 * d;
   const bf16* kb = c_mp.xkv + l * xkv_l + ((size_t)b * F + f0) * fstride + h * 64;
   float* sp = base + 64;
-  float* so = base + 64 + 500 + 4;
-  const float2 ml = group_attend<128, 8>(c_mp.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base, sp,
-                                         base + 64 + 500, so);
+  float* so = base + 64 + 512 + 32;
+#ifdef CW_XKV_HM_TIMING  // timing experiment only: head-major rows [b][h][k|v][f][64] over the same buffer
+  const bf16* kb_hm = c_mp.xkv + l * xkv_l + ((size_t)(b * H + h) * 2 * F + f0) * 64;
+  const float2 ml = group_attend_pipe<128, kXRing>(c_mp.qbuf + (size_t)b * d + h * 64, kb_hm, kb_hm + (size_t)F * 64, 64, nf, gtid,
+                                                   1 + grp, base, sp, base + 64 + 512, base + 64 + 512 + 16, so, ring);
+#else
+  const float2 ml = group_attend_pipe<128, kXRing>(c_mp.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base,
+                                                   sp, base + 64 + 512, base + 64 + 512 + 16, so, ring);
+#endif
   const int slot = c_mp.align_map[l * H + h];
   float* part = c_mp.xpart + ((size_t)task * kXSplit + split) * 66;
   if (gtid < 64) part[2 + gtid] = so[gtid];
   if (gtid == 0) { part[0] = ml.x; part[1] = ml.y; }
   if (slot >= 0) {
     float* sc = c_mp.xscore + (size_t)task * F + f0;
-    for (int j = gtid; j < nf; j += 128) sc[j] = sp[j];
+    for (int j = gtid; j < nf; j += 128) sc[j] = ex2_approx(sp[j] - ml.x);
   }
   __threadfence();
   named_bar(1 + grp, 128);
@@ -532,7 +430,7 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
     const float m0 = ld_cg(pt), m1 = ld_cg(pt + 66), m2 = ld_cg(pt + 132);
     const float l0 = ld_cg(pt + 1), l1 = ld_cg(pt + 67), l2 = ld_cg(pt + 133);
     const float M = fmaxf(m0, fmaxf(m1, m2));
-    const float w0 = expf(m0 - M), w1 = expf(m1 - M), w2 = expf(m2 - M);
+    const float w0 = ex2_approx(m0 - M), w1 = ex2_approx(m1 - M), w2 = ex2_approx(m2 - M);  // log2-domain maxima
     const float inv = 1.f / (l0 * w0 + l1 * w1 + l2 * w2);
     if (gtid < 64) {
       const float v = ld_cg(pt + 2 + gtid) * w0 + ld_cg(pt + 68 + gtid) * w1 + ld_cg(pt + 134 + gtid) * w2;
@@ -565,23 +463,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_mega_kernel() {
   unsigned long long t_prev = 0;
   mega_tick(-1, t_prev);
   const int n_ph = c_mp.n_phases;
-  const int pf = c_mp.l2pf;
-  bool have_pre = false;
 #pragma unroll 1
   for (int ph = 0; ph < n_ph; ++ph) {
     const PhaseDesc* D = c_mp.prog + ph;
     const int type = D->type;
-    if (pf > 0) {  // operand of phase ph+pf -> L2; past the end of the program: the first phases of the next step
-      const int q = ph + pf;
-      if (q < n_ph) l2_prefetch_phase(c_mp.prog + q, pos);
-      else l2_prefetch_phase(c_mp.prog + (q - n_ph), pos + 1);
-    }
-    if (type == PH_GEMV) ph_gemv(D, pos, have_pre);
+    if (type == PH_GEMV) ph_gemv(D, pos);
     else if (type == PH_CROSS_ATTN) ph_cross_attn(D->l, pos, s_flag);
     else if (type == PH_SELF_ATTN) ph_self_attn(D->l, pos);
     else ph_embed(pos);
-    have_pre = false;
-    if (c_mp.prefetch && ph + 1 < n_ph && D[1].type == PH_GEMV) have_pre = gemv_prefetch(D + 1);
     const int slot = D->dbg_slot;
     mega_tick(2 * slot, t_prev);
     grid_barrier(c_mp.bar, ((unsigned int)pos * (unsigned int)n_ph + (unsigned int)ph + 1u) * gridDim.x);

@@ -11,9 +11,11 @@ cfg = Wt.large_v3_config()
 eng.load_weights(Wt.synthetic_weights(cfg, eng.device, seed=0))
 xkv = (torch.randn(32, B, 1500, 2, 20, 64, device="cuda") * 0.5).to(torch.bfloat16)
 prompt = torch.tensor([[50258, 50259, 50360]] * B, dtype=torch.int32, device="cuda")
-for name, fl, env in (("mega (default)", 0, "0"), ("mega +prefetch", 0, "1"), ("mega eager", L.CW_DEC_NO_GRAPH, "0"),
-                      ("ops graph+pdl", L.CW_DEC_NO_MEGA, "0"), ("ops eager+pdl", L.CW_DEC_NO_MEGA | L.CW_DEC_NO_GRAPH, "0")):
-    os.environ["CW_MEGA_PREFETCH"] = env
+CASES = (("mega (default)", 0), ("mega eager", L.CW_DEC_NO_GRAPH), ("ops graph+pdl", L.CW_DEC_NO_MEGA),
+         ("ops eager+pdl", L.CW_DEC_NO_MEGA | L.CW_DEC_NO_GRAPH))
+if os.environ.get("ONLY_MEGA"):
+    CASES = CASES[:1]
+for name, fl in CASES:
     flags = L.CW_DEC_SUPPRESS_EOS | fl
     for _ in range(2):
         eng.decode(xkv, prompt, T, flags=flags, want_align=True)
