@@ -100,10 +100,17 @@ class AutomaticSpeechRecognitionPipeline:
         gk.update(generate_kwargs or {})
         bs = self.batch_size if batch_size is None else max(1, int(batch_size))
         cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
-        waves = [A.normalize_input(x) for x in items]
+        waves = [A.normalize_input(x, self._resample) for x in items]
         per_input = self._run(waves, cl, bs, gk)
         results = [self._postprocess(mo, rt) for mo in per_input]
         return results if is_list else results[0]
+
+    def _resample(self, x: np.ndarray, sr_in: int) -> np.ndarray:
+        """Host waveform at sr_in -> 16 kHz through cw_resample (HF preprocess :394-408 calls torchaudio here)."""
+        dev = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.engine.device)
+        out = self.engine.resample(dev, sr_in, A.SAMPLING_RATE)
+        self.engine.sync()
+        return out.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------------------
     def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict) -> List[List[Dict]]:

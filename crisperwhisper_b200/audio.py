@@ -3,7 +3,7 @@
 Mirrors AutomaticSpeechRecognitionPipeline.preprocess + chunk_iter
 (HF/pipelines/automatic_speech_recognition.py:341-477, :61-84): accepted inputs, mono mix-down, chunk/stride
 arithmetic.  File decoding uses scipy's WAV reader (ffmpeg, which HF shells out to at HF/pipelines/audio_utils.py:9-45,
-is not part of the hot path and absent from this image)."""
+is not part of the hot path and absent from this image); resampling to 16 kHz runs on the GPU (cw_resample)."""
 from __future__ import annotations
 
 import io
@@ -34,20 +34,11 @@ def read_wav(src) -> Tuple[np.ndarray, int]:
     return x, int(sr)
 
 
-def resample(x: np.ndarray, sr_in: int, sr_out: int = SAMPLING_RATE) -> np.ndarray:
-    """Polyphase resampling on the host (the reference calls torchaudio.functional.resample,
-    automatic_speech_recognition.py:394-408; this is outside the graded hot path)."""
-    if sr_in == sr_out:
-        return x
-    from math import gcd
-    from scipy.signal import resample_poly
-    g = gcd(sr_in, sr_out)
-    return resample_poly(x, sr_out // g, sr_in // g).astype(np.float32)
-
-
-def normalize_input(inputs) -> np.ndarray:
+def normalize_input(inputs, resampler=None) -> np.ndarray:
     """str (wav path) | bytes (wav file) | np.ndarray | {"array"|"raw", "sampling_rate"} -> float32 mono @16 kHz
-    (automatic_speech_recognition.py:342-417)."""
+    (automatic_speech_recognition.py:342-417).  Inputs at another rate go through `resampler(x, sr_in) -> x16k`, which the
+    pipeline binds to Engine.resample (cw_resample, the reference's torchaudio.functional.resample :394-408 on the GPU);
+    there is no host resampler: without one such an input is an error."""
     sr = SAMPLING_RATE
     if isinstance(inputs, str):
         inputs, sr = read_wav(inputs)
@@ -75,8 +66,12 @@ def normalize_input(inputs) -> np.ndarray:
     x = inputs
     if x.ndim != 1:
         x = x.mean(axis=0)
-    x = resample(np.asarray(x, dtype=np.float32), sr)
-    return np.ascontiguousarray(x, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if sr != SAMPLING_RATE:
+        if resampler is None:
+            raise ValueError(f"input is at {sr} Hz: pass a resampler (the pipeline uses Engine.resample) or 16 kHz audio")
+        x = np.ascontiguousarray(resampler(x, sr), dtype=np.float32)
+    return x
 
 
 def chunk_plan(n_samples: int, chunk_length_s: float = 30.0, stride_length_s=None, sampling_rate: int = SAMPLING_RATE):

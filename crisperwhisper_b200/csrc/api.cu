@@ -43,6 +43,10 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
                const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out, float* logits_out,
                int32_t* argmax_out, int* steps_out_host, void* ws, size_t ws_bytes, cudaStream_t st);
 void decode_state_free(cw_ctx* ctx);
+long long resample_out_len(long long n_in, int sr_in, int sr_out);
+size_t resample_workspace_bytes(int sr_in, int sr_out);
+int resample_run(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
 
 }  // namespace cw
 
@@ -222,6 +226,17 @@ int cw_layernorm(cw_ctx* ctx, const float* x, const float* gamma, const float* b
   CW_REQUIRE(ctx, CW_ERR_INVALID, "cw_layernorm: ctx is NULL");
   CW_CUDA(cudaSetDevice(ctx->device));
   return layernorm_run(ctx, x, gamma, beta, out_bf16, M, d, (cudaStream_t)stream);
+}
+
+long long cw_resample_out_len(long long n_in, int sr_in, int sr_out) { return resample_out_len(n_in, sr_in, sr_out); }
+
+size_t cw_resample_workspace_bytes(int sr_in, int sr_out) { return resample_workspace_bytes(sr_in, sr_out); }
+
+int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
+                size_t ws_bytes, void* stream) {
+  CW_REQUIRE(ctx, CW_ERR_INVALID, "cw_resample: ctx is NULL");
+  CW_CUDA(cudaSetDevice(ctx->device));
+  return resample_run(ctx, x, n_in, sr_in, sr_out, out, n_out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 long long cw_launch_count(const cw_ctx* ctx) { return ctx ? ctx->launches : 0; }

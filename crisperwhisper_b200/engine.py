@@ -133,6 +133,24 @@ class Engine:
                                        _p(frames), _p(ws), ws.numel(), self._sp()), "cw_logmel")
         return feats, tm, frames
 
+    # -- audio front-end -------------------------------------------------------------------------------------
+    def resample(self, wave: torch.Tensor, sr_in: int, sr_out: int = 16000) -> torch.Tensor:
+        """f32 [n] at sr_in -> f32 [ceil(n * sr_out / sr_in)] at sr_out on the device (cw_resample: the sinc/Hann
+        interpolation torchaudio.functional.resample applies in the reference's preprocess)."""
+        assert wave.is_cuda and wave.dtype == torch.float32 and wave.dim() == 1
+        wave = wave.contiguous()
+        n_in = wave.numel()
+        n_out = int(self.lib.cw_resample_out_len(n_in, int(sr_in), int(sr_out)))
+        if n_out < 0:
+            raise ValueError(f"resample: bad rates {sr_in} -> {sr_out}")
+        with self._on_stream():
+            out = torch.empty(n_out, dtype=torch.float32, device=self.device)
+            nb = self.lib.cw_resample_workspace_bytes(int(sr_in), int(sr_out))
+            ws = self._workspace("resample", max(nb, 256))
+            L.check(self.lib.cw_resample(self._h, _p(wave), n_in, int(sr_in), int(sr_out), _p(out), n_out, _p(ws), ws.numel(),
+                                         self._sp()), "cw_resample")
+        return out
+
     # -- stage 2a ----------------------------------------------------------------------------------------
     def encode(self, feats_tm: torch.Tensor, want_enc_out: bool = False):
         """feats_tm bf16 [B, 3002, 128] -> xkv bf16 [L_dec, B, 1500, 2, H, 64] (and enc_out bf16 [B,1500,d])."""

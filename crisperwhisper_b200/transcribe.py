@@ -28,6 +28,7 @@ def main():
     parser = argparse.ArgumentParser(description="Transcribe an audio file.")
     parser.add_argument("--f", type=str, required=True, help="Path to the audio file")
     parser.add_argument("--model_id", type=str, default="nyrahealth/CrisperWhisper")
+    parser.add_argument("--vtt", type=str, default=None, help="also write the word timestamps as WebVTT (REF/app.py:74-82)")
     args = parser.parse_args()
     if not os.path.exists(args.f):
         print(f"Error: The file '{args.f}' does not exist.")
@@ -36,6 +37,10 @@ def main():
         transcription = transcribe_audio(args.f, args.model_id)
         print("Transcription:")
         print(transcription["text"])
+        if args.vtt:
+            from .utils import timestamps_to_vtt
+            with open(args.vtt, "w", encoding="utf-8") as f:
+                f.write(timestamps_to_vtt(transcription["chunks"]))
     except Exception as e:  # same error contract as the reference CLI (REF/transcribe.py:46-52)
         print(f"An error occurred while transcribing the audio: {str(e)}")
         sys.exit(1)

@@ -1,4 +1,4 @@
-"""Post-processing helper with the reference's name and behaviour (REF/utils.py:1-29).
+"""Post-processing helpers with the reference's names and behaviour (REF/utils.py:1-29, REF/app.py:74-82).
 
 `adjust_pauses_for_hf_pipeline_output(pipeline_output, split_threshold=0.12)` redistributes the silence between
 adjacent word chunks: a pause `p = next_start - cur_end > 0` is shared evenly, `min(p, split_threshold) / 2` being added
@@ -21,3 +21,18 @@ def adjust_pauses_for_hf_pipeline_output(pipeline_output, split_threshold=0.12):
             nxt["timestamp"] = (nxt_start - share, nxt_end)
     pipeline_output["chunks"] = words
     return pipeline_output
+
+
+def _vtt_time(t: float) -> str:
+    # h:mm:ss.mmm with unpadded hours; the seconds field is rounded to the millisecond on its own (so 59.9996 prints as
+    # "60.000" without carrying into the minutes) — as REF/app.py:79-80 formats it
+    return f"{int(t // 3600)}:{int(t // 60 % 60):02d}:{t % 60:06.3f}"
+
+
+def timestamps_to_vtt(timestamps) -> str:
+    """Word chunks [{"text", "timestamp": (start, end)}, ...] -> WebVTT text, one cue per word (REF/app.py:74-82)."""
+    cues = ["WEBVTT\n\n"]
+    for word in timestamps:
+        start, end = word["timestamp"]
+        cues.append(f"{_vtt_time(start)} --> {_vtt_time(end)}\n{word['text']}\n\n")
+    return "".join(cues)

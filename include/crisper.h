@@ -228,6 +228,18 @@ int cw_attention_enc(cw_ctx* ctx, const void* qkv, void* out, int B, int S, int 
 /* LayerNorm f32 [M, d] -> bf16 [M, d], eps 1e-5 (modeling_whisper.py:393). */
 int cw_layernorm(cw_ctx* ctx, const float* x, const float* gamma, const float* beta, void* out_bf16, int M, int d,
                  void* stream);
+/* ---- audio front-end (SURVEY 8f "next" row 2): band-limited resampling of a mono waveform to the model rate.
+ *      Replaces torchaudio.functional.resample(x, sr_in, 16000) as AutomaticSpeechRecognitionPipeline.preprocess calls
+ *      it (HF/pipelines/automatic_speech_recognition.py:394-408): sinc interpolation, Hann window,
+ *      lowpass_filter_width 6, rolloff 0.99; the filter table is evaluated in double precision per call.
+ *  x    f32 [n_in] (device)      out  f32 [n_out] (device), n_out == cw_resample_out_len(n_in, sr_in, sr_out)
+ *  ws   >= cw_resample_workspace_bytes(sr_in, sr_out)  (device; holds the [taps][sr_out/gcd] filter table)
+ *  Synchronises the stream once (the table is staged from pageable host memory).  Rate pairs whose table would
+ *  exceed 256 MB (tiny common divisor) return CW_ERR_UNSUPPORTED. */
+long long cw_resample_out_len(long long n_in, int sr_in, int sr_out);
+size_t cw_resample_workspace_bytes(int sr_in, int sr_out);
+int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
+                size_t ws_bytes, void* stream);
 /* Number of kernel launches issued by this ctx since creation (bench.py `gpu_launches`). */
 long long cw_launch_count(const cw_ctx* ctx);
 /* Device time of the most recent call's dominant kernel is measured by the caller with events; these let

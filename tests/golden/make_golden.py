@@ -224,7 +224,47 @@ def gen_pipeline():
         json.dump(out, f, indent=1)
 
 
+def gen_resample():
+    """torchaudio.functional.resample (the call at HF/pipelines/automatic_speech_recognition.py:403-407) on seeded inputs."""
+    import torch
+    from torchaudio import functional as F
+    out = {}
+    cases = [(44100, 16000, 9000), (48000, 16000, 4801), (8000, 16000, 3000), (22050, 16000, 7001), (11025, 16000, 2000),
+             (16000, 16000, 500), (32000, 16000, 1), (24000, 16000, 37)]
+    for i, (sr, tgt, n) in enumerate(cases):
+        rng = np.random.default_rng(100 + i)
+        tt = np.arange(n) / sr
+        x = (0.4 * np.sin(2 * np.pi * 440.0 * tt) + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        y = F.resample(torch.from_numpy(x), sr, tgt).numpy()
+        out[f"c{i}_x"] = x
+        out[f"c{i}_y"] = y.astype(np.float32)
+        out[f"c{i}_sr"] = np.array([sr, tgt], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "resample_ta.npz"), **out)
+    print("resample_ta.npz", len(cases))
+
+
+def gen_vtt():
+    """REF/app.py:74-82 `timestamps_to_vtt` — app.py imports streamlit/moviepy (absent), so the function is lifted out of
+    the file with ast and executed on its own."""
+    import ast
+    src = open("/root/reference/app.py").read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "timestamps_to_vtt"][0]
+    ns = {}
+    exec("from typing import Any, Dict, List, Union\n" + ast.get_source_segment(src, fn), ns)
+    cases = {
+        "empty": [],
+        "one": [{"text": " hello", "timestamp": (0.0, 0.5)}],
+        "minutes": [{"text": "a", "timestamp": (59.9996, 60.0)}, {"text": "b", "timestamp": (61.25, 125.5)}],
+        "hours": [{"text": "x", "timestamp": (3599.9994, 3600.001)}, {"text": "y", "timestamp": (7325.125, 36000.0)}],
+        "unicode": [{"text": " [UH]", "timestamp": (1.1, 1.23)}, {"text": " \u4f60\u597d", "timestamp": (1.23, 2.0)}],
+    }
+    out = {k: {"input": v, "output": ns["timestamps_to_vtt"](v)} for k, v in cases.items()}
+    with open(os.path.join(HERE, "vtt_ref.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("vtt_ref.json", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["align", "logmel", "logits", "pauses", "pipeline"]
+    which = sys.argv[1:] or ["align", "logmel", "logits", "pauses", "pipeline", "resample", "vtt"]
     for w in which:
         globals()["gen_" + w]()

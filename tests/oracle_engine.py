@@ -9,6 +9,7 @@ import torch
 
 from oracle import align as OA
 from oracle import logmel as LM
+from oracle import resample as RS
 from oracle import whisper_ref as R
 
 
@@ -20,6 +21,9 @@ class OracleEngine:
 
     def sync(self):
         pass
+
+    def resample(self, wave, sr_in, sr_out=16000):
+        return torch.from_numpy(RS.resample(wave.numpy(), int(sr_in), int(sr_out)))
 
     def logmel(self, wave, mel_filters, n_valid=None, want_f32=True, want_tm=True):
         w = wave.numpy()

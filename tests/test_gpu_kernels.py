@@ -149,3 +149,53 @@ def test_attention_enc(engine, B, S, H):
     q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
     ref = (torch.softmax(q @ k.transpose(2, 3), -1) @ v).transpose(1, 2).reshape(B * S, d)
     assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+def test_resample_vs_torchaudio_golden_and_oracle(engine):
+    """cw_resample vs (a) torchaudio.functional.resample vectors (tests/golden/resample_ta.npz; the reference's preprocess
+    call) and (b) oracle/resample.py: max abs err < 5e-5 / 2e-6 on amplitude ~0.5 signals; lengths equal;
+    sr_in == sr_out and empty inputs pass through."""
+    from oracle import resample as RS
+    g = np.load(os.path.join(GOLDEN, "resample_ta.npz"))
+    n_cases = len([k for k in g.files if k.endswith("_x")])
+    for i in range(n_cases):
+        x, y, sr = g[f"c{i}_x"], g[f"c{i}_y"], g[f"c{i}_sr"]
+        got = engine.resample(torch.from_numpy(x).cuda(), int(sr[0]), int(sr[1]))
+        engine.sync()
+        got = got.cpu().numpy()
+        assert got.shape == y.shape, (i, got.shape, y.shape)
+        if y.size:
+            assert np.abs(got - y).max() < 5e-5, (i, "vs torchaudio", np.abs(got - y).max())
+            assert np.abs(got - RS.resample(x, int(sr[0]), int(sr[1]))).max() < 2e-6, (i, "vs oracle")
+    e = engine.resample(torch.zeros(0, dtype=torch.float32).cuda(), 44100, 16000)
+    assert e.numel() == 0
+
+
+def test_resample_full_size_sine_property(engine):
+    """30 s at 44.1 kHz -> 16 kHz (1 323 000 -> 480 000 samples): an in-band sine comes out as the same sine sampled at
+    16 kHz (band-limited interpolation), |err| < 2e-3 away from the zero-padded edges; length = ceil(n * 160 / 441)."""
+    sr, n = 44100, 44100 * 30
+    t = np.arange(n, dtype=np.float64) / sr
+    x = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    y = engine.resample(torch.from_numpy(x).cuda(), sr, 16000)
+    engine.sync()
+    y = y.cpu().numpy()
+    assert y.shape == (480000,)
+    want = 0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(480000) / 16000.0)
+    assert np.abs(y[200:-200] - want[200:-200]).max() < 2e-3
+
+
+def test_pipeline_resamples_other_rates(engine):
+    """normalize_input routes a non-16 kHz dict input through cw_resample (HF preprocess :394-408)."""
+    from crisperwhisper_b200 import audio as A
+    from oracle import resample as RS
+    x = (np.random.default_rng(3).standard_normal(8000) * 0.1).astype(np.float32)
+
+    def rs(w, sr_in):
+        out = engine.resample(torch.from_numpy(w).cuda(), sr_in, 16000)
+        engine.sync()
+        return out.cpu().numpy()
+    got = A.normalize_input({"array": x, "sampling_rate": 8000}, rs)
+    assert got.shape == (16000,) and np.abs(got - RS.resample(x, 8000, 16000)).max() < 2e-6
+    with pytest.raises(ValueError):
+        A.normalize_input({"array": x, "sampling_rate": 8000})

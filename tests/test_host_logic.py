@@ -106,3 +106,17 @@ def test_weight_packing_roundtrip_shapes():
     assert torch.equal(slots["CONV1_W"].view(d, 3, 128)[:, 1, :80].float(), w[:, :, 1].to(torch.bfloat16).float())
     assert torch.count_nonzero(slots["CONV1_W"].view(d, 3, 128)[:, :, 80:]) == 0
     assert slots["TOK_EMB"].shape[0] % 128 == 0 and torch.count_nonzero(slots["TOK_EMB"][cfg["vocab"]:]) == 0
+
+
+def test_timestamps_to_vtt_matches_reference_golden():
+    """crisperwhisper_b200.utils.timestamps_to_vtt == REF/app.py:74-82 on tests/golden/vtt_ref.json (generated from the
+    reference function): unpadded hours, per-field rounding of the seconds, one cue per word."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from crisperwhisper_b200.utils import timestamps_to_vtt
+    with open(os.path.join(GOLDEN, "vtt_ref.json")) as f:
+        g = json.load(f)
+    assert len(g) >= 5
+    for name, case in g.items():
+        assert timestamps_to_vtt(case["input"]) == case["output"], name

@@ -43,3 +43,31 @@ def test_host_logic_on_oracle_engine_matches_reference_pipeline(name):
     adj = adjust_pauses_for_hf_pipeline_output(copy.deepcopy(out))
     assert [tuple(c["timestamp"]) for c in adj["chunks"]] == [tuple(c["timestamp"]) for c in g["adjusted"]["chunks"]]
     assert pipe.last_stats["generate_passes"] >= 1
+
+
+def test_inputs_at_other_rates_go_through_the_engine_resampler():
+    """{"array", "sampling_rate": 8000} and a WAV file at 8 kHz are resampled by engine.resample (cw_resample on the GPU;
+    here the oracle) before chunking: same result as feeding the resampled 16 kHz array (HF preprocess :394-408)."""
+    import io
+    from scipy.io import wavfile
+    from oracle_engine import OracleEngine
+    from oracle import hf_harness as H
+    from oracle import resample as RS
+    from crisperwhisper_b200 import pipeline
+    from crisperwhisper_b200 import weights as Wt
+    m = H.build_model(H.tiny_hf_config(n_mels=80), seed=1, logit_scale=8.0, pos_scale=20.0)
+    cfg = Wt.config_from_hf(m)
+    cfg["lang_id"], cfg["task_id"] = H.TOK_IDS["en"], H.TOK_IDS["transcribe"]
+    eng = OracleEngine({k: v.float() for k, v in m.state_dict().items()}, cfg)
+    pipe = pipeline("automatic-speech-recognition", model=eng, tokenizer=H.synthetic_tokenizer(), chunk_length_s=30,
+                    batch_size=1, return_timestamps="word")
+    x8 = H.speechlike(9, 3 * 8000)
+    gk = {"max_new_tokens": 6}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = pipe({"array": x8.copy(), "sampling_rate": 8000}, generate_kwargs=gk)
+        b = pipe(RS.resample(x8, 8000, 16000), generate_kwargs=gk)
+        buf = io.BytesIO()
+        wavfile.write(buf, 8000, x8)
+        c = pipe(buf.getvalue(), generate_kwargs=gk)
+    assert a == b == c
