@@ -20,6 +20,7 @@
 // One decode step is captured once into a CUDA graph; the position lives in device memory, so the same graph is
 // replayed for every step (cudaGraphLaunch), with the host polling the "all finished" counter every 16 steps.
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -713,6 +714,7 @@ struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
   float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg; void* prog;
+  void* xunits; int* xsplits;
 };
 
 static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
@@ -732,7 +734,9 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.st = (DecState*)take(sizeof(DecState));
   t.finished = (int*)take((size_t)B * 4);
   t.seq = (int*)take((size_t)B * m.n_text_ctx * 4);
-  t.xpart = (float*)take((size_t)B * m.n_heads * kXSplit * 66 * 4);
+  t.xpart = (float*)take((size_t)B * m.n_heads * kXMaxSplit * 66 * 4);
+  t.xunits = take((size_t)4 * 1024 * sizeof(XUnit));   // up to 1024 CTAs
+  t.xsplits = (int*)take((size_t)B * m.n_heads * 4);
   t.xscore = (float*)take((size_t)B * m.n_heads * m.n_audio_ctx * 4);
   t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
   t.bar = (unsigned int*)take(256);
@@ -894,6 +898,40 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
 // weight batch before its LayerNorm (2.29 vs 2.26 ms/step). ncu: the warps wait on barriers and dependent loads (stall
 // barrier 11.4, long scoreboard 5.1 per issued instruction); HBM bandwidth and instruction fetch are not the limiters.
 
+// Cross-attention work units: every (sample, head) is cut into 3 or 4 equal frame ranges so that the grid's 4 x #CTA
+// group slots are (nearly) all used, then the ranges are dealt to the CTAs longest-first, each to the CTA that has streamed
+// the fewest frames so far and still has a free slot. With 160 tasks on 148 SMs: 112 tasks x 4 ranges of 375 frames + 48 x 3
+// of 500 = 592 units, 1500..1625 frames per CTA (a fixed 3-way cut gives 36 CTAs 2000 frames and the rest 1500).
+static int plan_cross_units(int tasks, int F, int n_cta, std::vector<XUnit>* units, std::vector<int>* splits) {
+  const int slots = 4 * n_cta;
+  if (3 * tasks > slots || n_cta > 1024) return -1;
+  int n4 = slots - 3 * tasks;
+  if (n4 > tasks) n4 = tasks;
+  if (F % 4 != 0 || F / 4 > kXMaxFrames) n4 = 0;
+  if (F % 3 != 0 || F / 3 > kXMaxFrames) return -1;
+  struct U { int task, split, f0, nf; };
+  std::vector<U> all;
+  splits->assign(tasks, 3);
+  for (int t = 0; t < tasks; ++t) {
+    const int ns = (t < n4) ? 4 : 3;
+    (*splits)[t] = ns;
+    for (int i = 0; i < ns; ++i) all.push_back({t, i, i * (F / ns), F / ns});
+  }
+  std::stable_sort(all.begin(), all.end(), [](const U& a, const U& b) { return a.nf > b.nf; });
+  units->assign((size_t)slots, XUnit{-1, 0, 0, 0});
+  std::vector<int> load(n_cta, 0), used(n_cta, 0);
+  for (const U& u : all) {
+    int best = -1;
+    for (int c = 0; c < n_cta; ++c)
+      if (used[c] < 4 && (best < 0 || load[c] < load[best])) best = c;
+    if (best < 0) return -1;
+    (*units)[(size_t)best * 4 + used[best]] = XUnit{u.task, u.split, u.f0, u.nf};
+    load[best] += u.nf;
+    used[best] += 1;
+  }
+  return 0;
+}
+
 // fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
 static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
                               const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
@@ -907,6 +945,17 @@ static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv
   p.st = bf.st; p.seq = bf.seq; p.xkv = xkv; p.align_map = ctx->d_align_map; p.align_out = align_out;
   p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
   p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.bar = bf.bar;
+  {
+    std::vector<XUnit> units;
+    std::vector<int> splits;
+    CW_REQUIRE(plan_cross_units(B * m.n_heads, m.n_audio_ctx, ctx->sm_count, &units, &splits) == 0, CW_ERR_UNSUPPORTED,
+               "decode megakernel: cannot lay out %d cross-attention tasks on %d CTAs", B * m.n_heads, ctx->sm_count);
+    CW_CUDA(cudaMemcpyAsync(bf.xunits, units.data(), units.size() * sizeof(XUnit), cudaMemcpyHostToDevice, st));
+    CW_CUDA(cudaMemcpyAsync(bf.xsplits, splits.data(), splits.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CW_CUDA(cudaStreamSynchronize(st));  // the vectors die at the end of this block
+    p.xunits = (const XUnit*)bf.xunits;
+    p.xsplits = bf.xsplits;
+  }
   p.dbg = getenv("CW_MEGA_DEBUG") ? bf.dbg : nullptr;
   SampleParams& sp = p.sp;
   sp.logits = bf.logits; sp.suppress = ctx->d_suppress; sp.seq = bf.seq; sp.seq_ld = m.n_text_ctx;
@@ -965,7 +1014,7 @@ static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
   const size_t smem_attn = (size_t)4 * 2048 * 4 + (size_t)4 * kXRing * 2 * 128 * 16;
   const size_t smem = smem_gemv > smem_attn ? smem_gemv : smem_attn;
   CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
-  CW_REQUIRE(m.n_text_ctx <= 1024 && m.n_audio_ctx <= kXSplit * 512, CW_ERR_UNSUPPORTED, "decode megakernel: context too long");
+  CW_REQUIRE(m.n_text_ctx <= 1024, CW_ERR_UNSUPPORTED, "decode megakernel: context too long");
   CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1032,7 +1081,8 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   g_use_pdl = !(flags & CW_DEC_NO_PDL);
   const bool profile = (flags & CW_DEC_PROFILE) != 0;
   // B <= 8: the whole step is one persistent cooperative kernel; otherwise (or on request) one kernel per operator
-  const bool use_mega = (B <= 8) && (m.d_model <= 1280) && !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
+  const bool use_mega = (B <= 8) && (m.d_model <= 1280) && (3 * B * m.n_heads <= 4 * ctx->sm_count) && (ctx->sm_count <= 1024) &&
+                        (m.n_audio_ctx % 3 == 0) && !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
   auto step_fn = [&](cw_ctx* c) -> int {
     if (use_mega) return enqueue_step_mega(c, st);
     return enqueue_step(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);

@@ -17,8 +17,12 @@
 
 static constexpr int kMegaThreads = 512;
 static constexpr int kMegaWarps = 16;
-static constexpr int kXSplit = 3;          // cross-attention frame splits per (sample, head)
-static constexpr int kXFrames = 500;       // frames per split (1500 / 3)
+static constexpr int kXMaxSplit = 4;       // cross-attention: a (sample, head) is cut into 3 or 4 frame ranges
+static constexpr int kXMaxFrames = 512;    // frames per range (smem score buffer)
+
+// One cross-attention work unit = one frame range of one (sample, head); the host lays units out over the
+// 4 group slots of every CTA so that all CTAs stream (nearly) the same number of encoder frames.
+struct XUnit { int task, split, f0, nf; };
 
 enum { PH_EMBED = 0, PH_GEMV = 1, PH_SELF_ATTN = 2, PH_CROSS_ATTN = 3 };
 
@@ -43,9 +47,11 @@ struct MegaParams {
   const int* align_map;      // [dec_layers * n_heads]
   float* align_out; int H_a, T_cap, n_prompt;
   // cross-attention merge scratch
-  float* xpart;              // [B*H][kXSplit][66]  (m, l, o[64])
-  float* xscore;             // [B*H][F] exp(score - m_split)
+  float* xpart;              // [B*H][kXMaxSplit][66]  (m, l, o[64])
+  float* xscore;             // [B*H][F] 2^(score - m_range)
   unsigned int* xcount;      // [B*H]
+  const XUnit* xunits;       // [gridDim.x * 4]; task < 0 = empty slot
+  const int* xsplits;        // [B*H] number of ranges of the task
   unsigned int* bar;         // grid barrier counter
   unsigned long long* dbg;   // optional [32]: per-phase compute / barrier-wait ns of CTA 0 (CW_MEGA_DEBUG)
   const struct PhaseDesc* prog; int n_phases;   // the step as a list of phases (built on the host once per call)
@@ -246,22 +252,28 @@ __device__ __forceinline__ float2 group_attend_pipe(const float* __restrict__ q6
                                                     float* sq, float* sp, float* smx /*[GT/8]*/, float* sl /*[GT/8]*/,
                                                     float* so /*[GT/8][64]*/, uint4* ring /*[D][2][GT]*/) {
   constexpr int G = GT / 8;
+  constexpr uint32_t kStageBytes = 2 * GT * 16;
   const int sub = gtid & 7, grp = gtid >> 3;
   const int n_it = (n + G - 1) / G;      // uniform over the group (and so over each of its warps)
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + gtid);
-  const bf16* krow = kb + (size_t)grp * row_stride + sub * 8;
-  const bf16* vrow = vb + (size_t)grp * row_stride + sub * 8;
+  // producer state: running global pointers / smem write address / row index (no per-iteration address arithmetic)
+  const bf16* kp = kb + (size_t)grp * row_stride + sub * 8;
+  const bf16* vp = vb + (size_t)grp * row_stride + sub * 8;
   const size_t it_stride = (size_t)G * row_stride;
-  int issue_it = 0, issue_slot = 0;
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring + gtid);
+  const uint32_t ring_e = ring_s + D * kStageBytes;
+  uint32_t wr = ring_s;
+  int jw = grp;
   auto issue = [&]() {
-    if (issue_it < n_it && grp + G * issue_it < n) {
-      const uint32_t dst = ring_s + (uint32_t)(issue_slot * 2 * GT * 16);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(krow + issue_it * it_stride) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + GT * 16), "l"(vrow + issue_it * it_stride) : "memory");
+    if (jw < n) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(wr), "l"(kp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(wr + GT * 16), "l"(vp) : "memory");
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    ++issue_it;
-    issue_slot = (issue_slot + 1 == D) ? 0 : issue_slot + 1;
+    kp += it_stride;
+    vp += it_stride;
+    jw += G;
+    wr += kStageBytes;
+    if (wr == ring_e) wr = ring_s;
   };
 #pragma unroll
   for (int st = 0; st < D - 1; ++st) issue();
@@ -274,20 +286,34 @@ __device__ __forceinline__ float2 group_attend_pipe(const float* __restrict__ q6
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  int slot = 0;
+  uint32_t rd = ring_s;
+  int j = grp;
+  float* spj = sp + grp;
+#pragma unroll 1
   for (int it = 0; it < n_it; ++it) {
     issue();  // refills the slot consumed in the previous iteration
     asm volatile("cp.async.wait_group %0;\n" ::"n"(D - 1) : "memory");
-    const int j = grp + G * it;
-    const uint4 ku = ring[(size_t)slot * 2 * GT + gtid];
-    const uint4 vu = ring[(size_t)slot * 2 * GT + GT + gtid];
-    slot = (slot + 1 == D) ? 0 : slot + 1;
-    float s = (j < n) ? dot8(ku, qv) : 0.f;
+    uint4 ku, vu;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ku.x), "=r"(ku.y), "=r"(ku.z), "=r"(ku.w) : "r"(rd) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(vu.x), "=r"(vu.y), "=r"(vu.z), "=r"(vu.w) : "r"(rd + GT * 16) : "memory");
+    rd += kStageBytes;
+    if (rd == ring_e) rd = ring_s;
+    const bool live = j < n;
+    // bf16 pair -> two floats with one shift and one mask (the low element sits in bits 0..15)
+    const uint32_t kw[4] = {ku.x, ku.y, ku.z, ku.w};
+    float s = 0.f;
+    if (live) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s = fmaf(qv[2 * e], __uint_as_float(kw[e] << 16), s);
+        s = fmaf(qv[2 * e + 1], __uint_as_float(kw[e] & 0xffff0000u), s);
+      }
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (j < n) {
-      if (sub == 0) sp[j] = s;
+    if (live) {
+      if (sub == 0) *spj = s;
       if (s > m) {  // new running maximum (rare after the first rows): rescale what has been accumulated
         const float sc = ex2_approx(m - s);
         m = s;
@@ -297,14 +323,15 @@ __device__ __forceinline__ float2 group_attend_pipe(const float* __restrict__ q6
       }
       const float pj = ex2_approx(s - m);
       l += pj;
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vu);
+      const uint32_t vw[4] = {vu.x, vu.y, vu.z, vu.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h2[e]);
-        acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
+        acc[2 * e] = fmaf(pj, __uint_as_float(vw[e] << 16), acc[2 * e]);
+        acc[2 * e + 1] = fmaf(pj, __uint_as_float(vw[e] & 0xffff0000u), acc[2 * e + 1]);
       }
     }
+    j += G;
+    spj += G;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   if (sub == 0) { smx[grp] = m; sl[grp] = l; }
@@ -386,29 +413,21 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
   const int d = c_mp.d, H = c_mp.n_heads, F = c_mp.F;
   const int warp = threadIdx.x >> 5;
   const int grp = warp >> 2, gtid = threadIdx.x & 127;
-  const int sub_id = blockIdx.x + gridDim.x * grp;
-  if (sub_id >= c_mp.B * H * kXSplit) return;
+  const XUnit un = c_mp.xunits[blockIdx.x * 4 + grp];
+  if (un.task < 0) return;
   float* base = sm_attn() + grp * 2048;     // sq[64] | sp[512] | max[16] | sum[16] | so[16*64]
   uint4* ring = reinterpret_cast<uint4*>(sm_attn() + 4 * 2048) + (size_t)grp * (kXRing * 2 * 128);
-  const int task = sub_id / kXSplit, split = sub_id - task * kXSplit;
+  const int task = un.task, split = un.split, f0 = un.f0, nf = un.nf;
   const int b = task / H, h = task - b * H;
-  const int f0 = split * kXFrames;
-  const int nf = min(kXFrames, F - f0);
   const size_t fstride = (size_t)2 * d;
   const size_t xkv_l = (size_t)c_mp.B * F * 2 * d;
   const bf16* kb = c_mp.xkv + l * xkv_l + ((size_t)b * F + f0) * fstride + h * 64;
   float* sp = base + 64;
   float* so = base + 64 + 512 + 32;
-#ifdef CW_XKV_HM_TIMING  // timing experiment only: head-major rows [b][h][k|v][f][64] over the same buffer
-  const bf16* kb_hm = c_mp.xkv + l * xkv_l + ((size_t)(b * H + h) * 2 * F + f0) * 64;
-  const float2 ml = group_attend_pipe<128, kXRing>(c_mp.qbuf + (size_t)b * d + h * 64, kb_hm, kb_hm + (size_t)F * 64, 64, nf, gtid,
-                                                   1 + grp, base, sp, base + 64 + 512, base + 64 + 512 + 16, so, ring);
-#else
   const float2 ml = group_attend_pipe<128, kXRing>(c_mp.qbuf + (size_t)b * d + h * 64, kb, kb + d, fstride, nf, gtid, 1 + grp, base,
                                                    sp, base + 64 + 512, base + 64 + 512 + 16, so, ring);
-#endif
   const int slot = c_mp.align_map[l * H + h];
-  float* part = c_mp.xpart + ((size_t)task * kXSplit + split) * 66;
+  float* part = c_mp.xpart + ((size_t)task * kXMaxSplit + split) * 66;
   if (gtid < 64) part[2 + gtid] = so[gtid];
   if (gtid == 0) { part[0] = ml.x; part[1] = ml.y; }
   if (slot >= 0) {
@@ -417,30 +436,50 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
   }
   __threadfence();
   named_bar(1 + grp, 128);
+  const int ns = c_mp.xsplits[task];
   if (gtid == 0) {
     const unsigned int old = atomicAdd(c_mp.xcount + task, 1u);
-    s_flag[grp] = (old == kXSplit - 1) ? 1 : 0;
-    if (old == kXSplit - 1) c_mp.xcount[task] = 0;
+    s_flag[grp] = (old == (unsigned int)(ns - 1)) ? 1 : 0;
+    if (old == (unsigned int)(ns - 1)) c_mp.xcount[task] = 0;
   }
   named_bar(1 + grp, 128);
-  if (s_flag[grp]) {  // last arriver: merge the three partial softmaxes
+  if (s_flag[grp]) {  // last arriver: merge the partial softmaxes of the task's ranges (log2-domain maxima)
     __threadfence();
-    const float* pt = c_mp.xpart + (size_t)task * kXSplit * 66;
-    static_assert(kXSplit == 3, "merge below is written for 3 splits");
-    const float m0 = ld_cg(pt), m1 = ld_cg(pt + 66), m2 = ld_cg(pt + 132);
-    const float l0 = ld_cg(pt + 1), l1 = ld_cg(pt + 67), l2 = ld_cg(pt + 133);
-    const float M = fmaxf(m0, fmaxf(m1, m2));
-    const float w0 = ex2_approx(m0 - M), w1 = ex2_approx(m1 - M), w2 = ex2_approx(m2 - M);  // log2-domain maxima
-    const float inv = 1.f / (l0 * w0 + l1 * w1 + l2 * w2);
+    const float* pt = c_mp.xpart + (size_t)task * kXMaxSplit * 66;
+    float mx[kXMaxSplit], w[kXMaxSplit];
+    float M = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kXMaxSplit; ++i) {
+      mx[i] = (i < ns) ? ld_cg(pt + i * 66) : -INFINITY;
+      M = fmaxf(M, mx[i]);
+    }
+    float L = 0.f;
+#pragma unroll
+    for (int i = 0; i < kXMaxSplit; ++i) {
+      w[i] = (i < ns) ? ex2_approx(mx[i] - M) : 0.f;
+      if (i < ns) L += ld_cg(pt + i * 66 + 1) * w[i];
+    }
+    const float inv = 1.f / L;
     if (gtid < 64) {
-      const float v = ld_cg(pt + 2 + gtid) * w0 + ld_cg(pt + 68 + gtid) * w1 + ld_cg(pt + 134 + gtid) * w2;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < kXMaxSplit; ++i)
+        if (i < ns) v += ld_cg(pt + i * 66 + 2 + gtid) * w[i];
       c_mp.attn[(size_t)b * d + h * 64 + gtid] = __float2bfloat16(v * inv);
     }
     const int s_row = pos - c_mp.n_prompt;
     if (slot >= 0 && c_mp.align_out != nullptr && s_row >= 0 && s_row < c_mp.T_cap) {
       float* dst = c_mp.align_out + (((size_t)b * c_mp.H_a + slot) * c_mp.T_cap + s_row) * F;
       const float* sc = c_mp.xscore + (size_t)task * F;
-      for (int j = gtid; j < F; j += 128) dst[j] = ld_cg(sc + j) * (j < kXFrames ? w0 : (j < 2 * kXFrames ? w1 : w2)) * inv;
+      const int per = F / ns;             // ranges of one task are equal (the host only cuts F into ns equal parts)
+#pragma unroll
+      for (int i = 0; i < kXMaxSplit; ++i) w[i] *= inv;
+#pragma unroll 1
+      for (int j = gtid; j < F; j += 128) {
+        const int i = j / per;
+        const float wi = (i == 0) ? w[0] : ((i == 1) ? w[1] : ((i == 2) ? w[2] : w[3]));
+        dst[j] = ld_cg(sc + j) * wi;
+      }
     }
   }
 }
