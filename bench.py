@@ -361,7 +361,7 @@ def main():
                 "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch, ncu --set full
                 # (profiles/r01_ncu_summary.md: 3.574 GB read + 11 MB written)
-                "traffic": 3622000000, "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
+                "traffic": 3619000000, "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
                 "algorithmic_bytes_per_launch": int(step_bytes), "avg_launch_ms": round(per_launch_ms, 4),
                 "launches_timed": n_launch * 3,
                 "bytes_breakdown_GB": {"decoder_weights": round(w_bytes / 1e9, 3), "cross_kv": round(xkv_bytes / 1e9, 3),
