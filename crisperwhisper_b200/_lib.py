@@ -61,6 +61,7 @@ EXPORTS = {
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cw_attention_enc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cw_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cw_decode_cross_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cw_resample_out_len": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
     "cw_resample_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cw_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,

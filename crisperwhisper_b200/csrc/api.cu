@@ -43,6 +43,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
                const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out, float* logits_out,
                int32_t* argmax_out, int* steps_out_host, void* ws, size_t ws_bytes, cudaStream_t st);
 void decode_state_free(cw_ctx* ctx);
+int decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out);
 long long resample_out_len(long long n_in, int sr_in, int sr_out);
 size_t resample_workspace_bytes(int sr_in, int sr_out);
 int resample_run(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
@@ -237,6 +238,10 @@ int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_o
   CW_REQUIRE(ctx, CW_ERR_INVALID, "cw_resample: ctx is NULL");
   CW_CUDA(cudaSetDevice(ctx->device));
   return resample_run(ctx, x, n_in, sr_in, sr_out, out, n_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int cw_decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out) {
+  return decode_cross_plan(tasks, n_frames, n_cta, units_out, splits_out);
 }
 
 long long cw_launch_count(const cw_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -932,6 +932,21 @@ static int plan_cross_units(int tasks, int F, int n_cta, std::vector<XUnit>* uni
   return 0;
 }
 
+// host-only view of the plan for tests (cw_decode_cross_plan): units_out [4 * n_cta][4] = {task, split, f0, nf}
+int decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out) {
+  std::vector<XUnit> units;
+  std::vector<int> splits;
+  CW_REQUIRE(tasks >= 1 && n_frames >= 1 && n_cta >= 1 && units_out && splits_out, CW_ERR_INVALID, "cw_decode_cross_plan: bad argument");
+  CW_REQUIRE(plan_cross_units(tasks, n_frames, n_cta, &units, &splits) == 0, CW_ERR_UNSUPPORTED,
+             "cw_decode_cross_plan: %d tasks x %d frames do not fit 4 x %d slots", tasks, n_frames, n_cta);
+  for (size_t i = 0; i < units.size(); ++i) {
+    units_out[4 * i] = units[i].task; units_out[4 * i + 1] = units[i].split;
+    units_out[4 * i + 2] = units[i].f0; units_out[4 * i + 3] = units[i].nf;
+  }
+  for (int t = 0; t < tasks; ++t) splits_out[t] = splits[t];
+  return CW_OK;
+}
+
 // fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
 static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
                               const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {

@@ -240,6 +240,11 @@ long long cw_resample_out_len(long long n_in, int sr_in, int sr_out);
 size_t cw_resample_workspace_bytes(int sr_in, int sr_out);
 int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
                 size_t ws_bytes, void* stream);
+/* Host-only introspection of the decode step kernel's cross-attention work split (no GPU needed; used by the CPU tests):
+ * `tasks` = B * n_heads (sample, head) pairs over n_frames encoder frames on n_cta persistent CTAs with 4 group slots each.
+ * units_out i32 [4 * n_cta][4] = {task, range index, first frame, frame count}, task < 0 = empty slot;
+ * splits_out i32 [tasks] = number of equal frame ranges of the task (3 or 4). CW_ERR_UNSUPPORTED if it does not fit. */
+int cw_decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out);
 /* Number of kernel launches issued by this ctx since creation (bench.py `gpu_launches`). */
 long long cw_launch_count(const cw_ctx* ctx);
 /* Device time of the most recent call's dominant kernel is measured by the caller with events; these let

@@ -45,3 +45,32 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("load() must raise when the CUDA library is missing")
+
+
+def test_cross_attention_plan_covers_and_balances():
+    """cw_decode_cross_plan (host-only): every (sample, head) task's frames are covered exactly once by 3 or 4 equal ranges,
+    no CTA gets more than 4 units, and at the bench shape (160 tasks x 1500 frames on 148 CTAs) the most loaded CTA streams
+    1625 frames (a fixed 3-way cut would give 2000)."""
+    import ctypes as C
+    import numpy as np
+    from crisperwhisper_b200 import _lib as L
+    lib = L.load()
+    for tasks, F, n_cta in ((160, 1500, 148), (6, 1500, 148), (100, 1500, 132), (197, 1500, 148), (1, 1500, 1)):
+        units = np.full((4 * n_cta, 4), -7, dtype=np.int32)
+        splits = np.zeros(tasks, dtype=np.int32)
+        rc = lib.cw_decode_cross_plan(tasks, F, n_cta, units.ctypes.data_as(C.c_void_p), splits.ctypes.data_as(C.c_void_p))
+        assert rc == 0, lib.cw_last_error()
+        used = units[units[:, 0] >= 0]
+        assert set(np.unique(splits)) <= {3, 4}
+        cover = np.zeros((tasks, F), dtype=np.int32)
+        for t, sp, f0, nf in used:
+            assert 0 <= sp < splits[t] and nf == F // splits[t] and f0 == sp * nf and nf <= 512
+            cover[t, f0:f0 + nf] += 1
+        assert (cover == 1).all()
+        per_cta = units[:, 3].reshape(n_cta, 4) * (units[:, 0].reshape(n_cta, 4) >= 0)
+        load = per_cta.sum(1)
+        assert load.max() <= int(np.ceil(tasks * F / n_cta)) + 500
+        if (tasks, n_cta) == (160, 148):
+            assert load.max() == 1625 and load.min() == 1500
+    bad = np.zeros((4 * 10, 4), dtype=np.int32)
+    assert lib.cw_decode_cross_plan(100, 1500, 10, bad.ctypes.data_as(C.c_void_p), np.zeros(100, np.int32).ctypes.data_as(C.c_void_p)) != 0
