@@ -474,11 +474,25 @@ __device__ __forceinline__ void ph_cross_attn(int l, int pos, int* s_flag) {
       const int per = F / ns;             // ranges of one task are equal (the host only cuts F into ns equal parts)
 #pragma unroll
       for (int i = 0; i < kXMaxSplit; ++i) w[i] *= inv;
-#pragma unroll 1
-      for (int j = gtid; j < F; j += 128) {
-        const int i = j / per;
-        const float wi = (i == 0) ? w[0] : ((i == 1) ? w[1] : ((i == 2) ? w[2] : w[3]));
-        dst[j] = ld_cg(sc + j) * wi;
+      // 12 independent L2 loads per thread in flight (a one-load-per-iteration loop would serialise 12 L2 round trips on
+      // the critical path of the phase: the merging group is by construction the last one of its task to finish)
+      constexpr int NB = 12;
+      for (int j0 = gtid; j0 < F; j0 += NB * 128) {
+        float vals[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int j = j0 + 128 * k;
+          vals[k] = (j < F) ? ld_cg(sc + j) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int j = j0 + 128 * k;
+          if (j < F) {
+            const int i = (j >= per) + (j >= 2 * per) + (j >= 3 * per);
+            const float wi = (i == 0) ? w[0] : ((i == 1) ? w[1] : ((i == 2) ? w[2] : w[3]));
+            dst[j] = vals[k] * wi;
+          }
+        }
       }
     }
   }
