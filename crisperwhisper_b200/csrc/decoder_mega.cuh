@@ -3,13 +3,16 @@
 // The multi-kernel step (decoder.cu) is latency-bound at small batch: 262 short dependent kernels per token.
 // Here the whole step — embed, 32 x {LN+qkv, self-attention, o-proj, LN+q_c, cross-attention, o_c-proj, LN+fc1+GELU, fc2},
 // final LN + logits, logits processors + argmax — runs in ONE launch of #SM CTAs x 512 threads that stay resident and
-// meet at grid-wide barriers (monotonic counter in global memory, bounded spin).  Work distribution per phase:
+// meet at grid-wide barriers (monotonic counter in global memory, red.release arrive + ld.acquire poll, bounded spin).
+// Work distribution per phase:
 //   projections   16-row tiles of the weight matrix; KW warps split K for one tile (mma.sync.m16n8k16, weights
 //                 streamed HBM -> A fragments exactly once), 16/KW tiles in flight per CTA, named barriers per group
-//   self-attn     one 8-warp group per (sample, head)
-//   cross-attn    (sample, head) split 3-way over the 1500 frames -> 480 four-warp groups <= 592 slots: one wave;
-//                 the group that arrives last at the per-(sample, head) counter merges the three partial softmaxes,
-//                 writes the head output and, for alignment heads, the normalised probabilities
+//   self-attn     one 8-warp group per (sample, head) over the KV-cache rows 0..pos
+//   cross-attn    every (sample, head) is cut into 3 or 4 equal frame ranges; the host deals the ranges to the 4 four-warp
+//                 group slots of each CTA so that all CTAs stream nearly the same number of frames (XUnit table); the
+//                 group that arrives last at the per-(sample, head) counter merges the partial softmaxes, writes the
+//                 head output and, for alignment heads, the normalised probabilities
+//   both attentions stream K/V rows through a per-thread cp.async ring (single pass, online softmax in the log2 domain)
 // Activations cross SMs between phases, so they are read with ld.global.cg (L2) — L1 is not coherent.
 // Supports B <= 8 (one n8 MMA tile); larger batches use the multi-kernel path.
 #pragma once
