@@ -120,3 +120,68 @@ def test_timestamps_to_vtt_matches_reference_golden():
     assert len(g) >= 5
     for name, case in g.items():
         assert timestamps_to_vtt(case["input"]) == case["output"], name
+
+
+def test_chunk_plan_matches_hf_chunk_iter_randomised():
+    """Random lengths, chunk lengths and stride pairs. HF's preprocess rounds chunk and strides to multiples of
+    `_align_to` = getattr(model.config, "inputs_to_logits_ratio", 1), which is 1 for a WhisperConfig
+    (automatic_speech_recognition.py:328-338,435-438): plain rounding to samples, as chunk_plan does."""
+    from transformers.pipelines.automatic_speech_recognition import chunk_iter
+    from crisperwhisper_b200 import audio as A
+
+    class FE:
+        sampling_rate = 16000
+
+        def __call__(self, chunk, **kw):
+            return {"n": len(chunk)}
+
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        n = int(rng.integers(1, 3_000_000))
+        chunk_s = float(rng.choice([5.0, 12.5, 30.0]))
+        sl = float(rng.choice([0.5, 1.0, chunk_s / 6]))
+        sr_ = float(rng.choice([0.5, 1.0, chunk_s / 6]))
+        align_to = 1
+        chunk_len = int(round(chunk_s * 16000 / align_to) * align_to)
+        left = int(round(sl * 16000 / align_to) * align_to)
+        right = int(round(sr_ * 16000 / align_to) * align_to)
+        x = np.zeros(n, np.float32)
+        ref = [(it["stride"], it["is_last"]) for it in chunk_iter(x, FE(), chunk_len, left, right)]
+        mine = [((ln, l, r), last) for (_, ln, l, r, last) in A.chunk_plan(n, chunk_s, (sl, sr_))]
+        assert mine == ref, (n, chunk_s, sl, sr_)
+
+
+def test_retrieve_segment_matches_hf_randomised():
+    """Random token streams over {text, timestamp} with random timestamp placement, seek window and time offset."""
+    from transformers.models.whisper.generation_whisper import WhisperGenerationMixin
+    from crisperwhisper_b200 import generate as G
+    ts_begin, n_prompt = 364, 3
+    rng = np.random.default_rng(11)
+    for case in range(300):
+        L = int(rng.integers(1, 24))
+        t = int(rng.integers(0, 200))
+        seq = []
+        for _ in range(L):
+            if rng.random() < 0.35:
+                t = min(1500, t + int(rng.integers(0, 120)))
+                seq.append(ts_begin + t)
+                if rng.random() < 0.5:
+                    seq.append(ts_begin + t)
+            else:
+                seq.append(int(rng.integers(0, 256)))
+        tt = (np.round(rng.uniform(0, 30, n_prompt + len(seq)) / 0.02) * 0.02).astype(np.float32)
+        seek_frames = int(rng.choice([3000, 2400, 1801, 600]))
+        off = float(rng.choice([0.0, 12.0, 29.98]))
+        ref_segs, ref_off = WhisperGenerationMixin._retrieve_segment(
+            seek_sequence=torch.tensor(seq), seek_outputs=[{"token_timestamps": torch.from_numpy(tt)}],
+            time_offset=torch.tensor([off], dtype=torch.float64), timestamp_begin=ts_begin,
+            seek_num_frames=torch.tensor([seek_frames]), time_precision=0.02, time_precision_features=0.01, input_stride=2,
+            prev_idx=0, idx=0, return_token_timestamps=True, decoder_input_ids=torch.zeros(1, n_prompt, dtype=torch.long))
+        segs, seg_off = G.retrieve_segment(np.array(seq), tt, off, ts_begin, seek_frames, n_prompt)
+        assert int(ref_off) == int(seg_off), (case, seq)
+        assert len(segs) == len(ref_segs), (case, seq)
+        for a, b in zip(segs, ref_segs):
+            assert a["tokens"].tolist() == b["tokens"].tolist(), (case, seq)
+            assert tuple(a["idxs"]) == tuple(b["idxs"])
+            assert float(a["start"]) == float(b["start"]) and float(a["end"]) == float(b["end"]), (case, seq)
+            assert np.array_equal(a["token_timestamps"], b["token_timestamps"].numpy()), (case, seq)
