@@ -73,6 +73,21 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("
 // before, and its reads after, the barrier (release/acquire are cumulative over the bar.sync). Bounded spin -> trap.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
+#ifdef CW_BAR_WARP_POLL
+  // Experiment for the next round (build with tools/build_variant.sh NAME -DCW_BAR_WARP_POLL, compare with tools/ab_run.sh):
+  // lane 0 of EVERY warp polls, so the second CTA-wide barrier goes away; acquire by lane 0 + __syncwarp orders the warp.
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+  if ((threadIdx.x & 31) == 0) {
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (++spins > (1u << 26)) __trap();
+    }
+  }
+  __syncwarp();
+#else
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int spins = 0;
@@ -84,9 +99,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
     }
   }
   __syncthreads();
+#endif
 }
 
-// ---- activation staging: rows of B samples -> bf16 [8][K+32] in smem --------------------------------------
 // LayerNorm of the B rows into xs (bf16). Warps 0..7 own one row each (values stay in registers between the statistics
 // and the normalisation); meanwhile warps 8..15 fetch gamma/beta into smem and signal named barrier 15 (arrive only),
 // so that round trip is off the rows' chain. Ends with a CTA-wide barrier: on return xs is complete.
