@@ -61,7 +61,9 @@ EXPORTS = {
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cw_attention_enc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cw_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "cw_decode_cross_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cw_decode_cross_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cw_decode_pack_bytes": (C.c_size_t, [C.c_void_p]),
+    "cw_decode_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cw_resample_out_len": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
     "cw_resample_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cw_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
@@ -90,7 +92,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export what include/crisper.h declares
         fn.restype = res
         fn.argtypes = args
-    if lib.cw_abi_version() != 1:
+    if lib.cw_abi_version() != 2:
         raise RuntimeError("libcrisper.so ABI version mismatch")
     _lib = lib
     return lib

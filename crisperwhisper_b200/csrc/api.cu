@@ -1,6 +1,7 @@
 // api.cu — extern "C" boundary of libcrisper.so (see include/crisper.h for the contract of every entry point).
 #include <stdarg.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -43,7 +44,10 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
                const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out, float* logits_out,
                int32_t* argmax_out, int* steps_out_host, void* ws, size_t ws_bytes, cudaStream_t st);
 void decode_state_free(cw_ctx* ctx);
-int decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out);
+int decode_cross_plan(int tasks, int n_frames, int chunk_rows, int n_cta, int32_t* items_out, int32_t* cta_off_out,
+                      int32_t* splits_out);
+size_t decode_pack_bytes(const cw_ctx* ctx);
+int decode_pack_run(cw_ctx* ctx, void* buf, size_t bytes, cudaStream_t st);
 long long resample_out_len(long long n_in, int sr_in, int sr_out);
 size_t resample_workspace_bytes(int sr_in, int sr_out);
 int resample_run(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
@@ -106,48 +110,61 @@ int cw_load_weights(cw_ctx* ctx, const void* const* dev_ptrs, int n_ptrs, const 
   CW_REQUIRE((d->median_filter_width & 1) && d->median_filter_width >= 1 && d->median_filter_width <= 15, CW_ERR_INVALID,
              "cw_load_weights: median_filter_width=%d", d->median_filter_width);
   for (int i = 0; i < n_ptrs; ++i) CW_REQUIRE(dev_ptrs[i] != nullptr, CW_ERR_INVALID, "cw_load_weights: slot %d is NULL", i);
+  CW_REQUIRE(d->n_align_heads == 0 || d->align_heads_host != nullptr, CW_ERR_INVALID, "cw_load_weights: align_heads_host is NULL");
+  // alignment-head lookup: (layer, head) -> slot. Everything is validated and built in locals first; ctx is only
+  // touched once nothing can fail any more except CUDA allocation, and then it is left without weights.
+  std::vector<int32_t> amap((size_t)d->dec_layers * d->n_heads, -1);
+  for (int i = 0; i < d->n_align_heads; ++i) {
+    int l = d->align_heads_host[2 * i], h = d->align_heads_host[2 * i + 1];
+    CW_REQUIRE(l >= 0 && l < d->dec_layers && h >= 0 && h < d->n_heads, CW_ERR_INVALID,
+               "cw_load_weights: alignment head (%d,%d) out of range", l, h);
+    CW_REQUIRE(amap[(size_t)l * d->n_heads + h] < 0, CW_ERR_INVALID, "cw_load_weights: alignment head (%d,%d) listed twice", l, h);
+    amap[(size_t)l * d->n_heads + h] = i;
+  }
+  std::vector<uint8_t> sup((size_t)d->vocab_padded, 0);
+  for (int i = 0; i < d->n_suppress; ++i) {
+    int t = d->suppress_host[i];
+    if (t >= 0 && t < d->vocab) sup[t] |= 1;
+  }
+  for (int i = 0; i < d->n_begin_suppress; ++i) {
+    int t = d->begin_suppress_host[i];
+    if (t >= 0 && t < d->vocab) sup[t] |= 2;
+  }
+  for (int t = d->vocab; t < d->vocab_padded; ++t) sup[t] |= 4;  // padding rows can never be sampled
   CW_CUDA(cudaSetDevice(ctx->device));
-
+  const void** h_w = (const void**)malloc(sizeof(void*) * n_ptrs);
+  CW_REQUIRE(h_w != nullptr, CW_ERR_INVALID, "cw_load_weights: out of host memory");
+  memcpy((void*)h_w, dev_ptrs, sizeof(void*) * n_ptrs);
+  const void** d_w = nullptr;
+  int32_t* d_amap = nullptr;
+  uint8_t* d_sup = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_w, sizeof(void*) * n_ptrs);
+  if (e == cudaSuccess) e = cudaMalloc(&d_amap, std::max<size_t>(amap.size(), 1) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_sup, sup.size());
+  if (e == cudaSuccess) e = cudaMemcpy((void*)d_w, dev_ptrs, sizeof(void*) * n_ptrs, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !amap.empty()) e = cudaMemcpy(d_amap, amap.data(), amap.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_sup, sup.data(), sup.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (d_w) cudaFree((void*)d_w);
+    if (d_amap) cudaFree(d_amap);
+    if (d_sup) cudaFree(d_sup);
+    free((void*)h_w);
+    return cuda_fail(e, "cw_load_weights: device tables");   // the previous weights (if any) stay loaded and intact
+  }
+  // swap in
+  decode_state_free(ctx);
   free((void*)ctx->w);
-  ctx->w = (const void**)malloc(sizeof(void*) * n_ptrs);
-  memcpy((void*)ctx->w, dev_ptrs, sizeof(void*) * n_ptrs);
-  ctx->n_w = n_ptrs;
   if (ctx->d_w) cudaFree((void*)ctx->d_w);
-  CW_CUDA(cudaMalloc((void**)&ctx->d_w, sizeof(void*) * n_ptrs));
-  CW_CUDA(cudaMemcpy((void*)ctx->d_w, dev_ptrs, sizeof(void*) * n_ptrs, cudaMemcpyHostToDevice));
+  if (ctx->d_align_map) cudaFree(ctx->d_align_map);
+  if (ctx->d_suppress) cudaFree(ctx->d_suppress);
+  ctx->w = h_w; ctx->n_w = n_ptrs; ctx->d_w = d_w; ctx->d_align_map = d_amap; ctx->d_suppress = d_sup;
+  ctx->pack_buf = nullptr;   // the fragment-major copies belong to the previous weights
   ModelDesc& m = ctx->md;
   m.d_model = d->d_model; m.n_heads = d->n_heads; m.enc_layers = d->enc_layers; m.dec_layers = d->dec_layers;
   m.ffn_dim = d->ffn_dim; m.vocab = d->vocab; m.vocab_padded = d->vocab_padded; m.n_mels = d->n_mels;
   m.n_audio_ctx = d->n_audio_ctx; m.n_text_ctx = d->n_text_ctx; m.eos_id = d->eos_id;
   m.no_timestamps_id = d->no_timestamps_id; m.max_initial_timestamp_index = d->max_initial_timestamp_index;
   m.median_filter_width = d->median_filter_width; m.n_align_heads = d->n_align_heads;
-
-  // alignment-head lookup: (layer, head) -> slot
-  std::vector<int32_t> amap((size_t)m.dec_layers * m.n_heads, -1);
-  for (int i = 0; i < d->n_align_heads; ++i) {
-    int l = d->align_heads_host[2 * i], h = d->align_heads_host[2 * i + 1];
-    CW_REQUIRE(l >= 0 && l < m.dec_layers && h >= 0 && h < m.n_heads, CW_ERR_INVALID,
-               "cw_load_weights: alignment head (%d,%d) out of range", l, h);
-    amap[(size_t)l * m.n_heads + h] = i;
-  }
-  if (ctx->d_align_map) cudaFree(ctx->d_align_map);
-  CW_CUDA(cudaMalloc(&ctx->d_align_map, amap.size() * sizeof(int32_t)));
-  CW_CUDA(cudaMemcpy(ctx->d_align_map, amap.data(), amap.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  // suppression masks
-  std::vector<uint8_t> sup((size_t)m.vocab_padded, 0);
-  for (int i = 0; i < d->n_suppress; ++i) {
-    int t = d->suppress_host[i];
-    if (t >= 0 && t < m.vocab) sup[t] |= 1;
-  }
-  for (int i = 0; i < d->n_begin_suppress; ++i) {
-    int t = d->begin_suppress_host[i];
-    if (t >= 0 && t < m.vocab) sup[t] |= 2;
-  }
-  for (int t = m.vocab; t < m.vocab_padded; ++t) sup[t] |= 4;  // padding rows can never be sampled
-  if (ctx->d_suppress) cudaFree(ctx->d_suppress);
-  CW_CUDA(cudaMalloc(&ctx->d_suppress, sup.size()));
-  CW_CUDA(cudaMemcpy(ctx->d_suppress, sup.data(), sup.size(), cudaMemcpyHostToDevice));
-  decode_state_free(ctx);
   ctx->has_weights = true;
   return CW_OK;
 }
@@ -240,8 +257,18 @@ int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_o
   return resample_run(ctx, x, n_in, sr_in, sr_out, out, n_out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int cw_decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out) {
-  return decode_cross_plan(tasks, n_frames, n_cta, units_out, splits_out);
+int cw_decode_cross_plan(int tasks, int n_frames, int chunk_rows, int n_cta, int32_t* items_out, int32_t* cta_off_out,
+                         int32_t* splits_out) {
+  return decode_cross_plan(tasks, n_frames, chunk_rows, n_cta, items_out, cta_off_out, splits_out);
+}
+
+size_t cw_decode_pack_bytes(const cw_ctx* ctx) { return (ctx && ctx->has_weights) ? decode_pack_bytes(ctx) : 0; }
+
+int cw_decode_pack(cw_ctx* ctx, void* buf, size_t bytes, void* stream) {
+  CW_REQUIRE(ctx, CW_ERR_INVALID, "cw_decode_pack: ctx is NULL");
+  CW_REQUIRE(ctx->has_weights, CW_ERR_STATE, "cw_decode_pack: call cw_load_weights first");
+  CW_CUDA(cudaSetDevice(ctx->device));
+  return decode_pack_run(ctx, buf, bytes, (cudaStream_t)stream);
 }
 
 long long cw_launch_count(const cw_ctx* ctx) { return ctx ? ctx->launches : 0; }

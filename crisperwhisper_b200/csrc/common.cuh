@@ -71,6 +71,7 @@ struct cw_ctx {
   long long launches;
   void* gemm_state;      // gemm.cu private (tensor-map cache)
   void* dec_state;       // decoder.cu private (graph cache)
+  const void* pack_buf;  // caller-owned fragment-major copies of the decoder matrices (cw_decode_pack)
   double prof_ms[4];     // CW_DEC_PROFILE accumulators
   long long prof_n[4];
 };

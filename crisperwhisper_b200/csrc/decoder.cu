@@ -32,7 +32,8 @@ enum { EPI_QKV = 0, EPI_F32 = 1, EPI_RESID = 2, EPI_GELU_BF16 = 3 };
 struct DecState {  // device-resident step state (ints)
   int pos;         // position being processed (input token index)
   int n_finished;
-  int pad[2];
+  unsigned int bar_epoch;  // grid barriers completed by the step kernel in this decode call
+  int pad;
 };
 
 struct GemvParams {
@@ -49,7 +50,7 @@ struct GemvParams {
   bf16* out_bf16;       // EPI_GELU_BF16                                       [B, N]
   bf16* kcache;         // EPI_QKV: [B, n_ctx, d] of this layer
   bf16* vcache;
-  int d, n_ctx;
+  int d, n_ctx, n_heads;
   const DecState* st;
 };
 
@@ -240,9 +241,13 @@ __global__ void __launch_bounds__(kGemvThreadsMax) gemv_kernel(GemvParams p) {
     } else {  // EPI_QKV
       const int d = p.d;
       const int pos = p.st->pos;
-      if (n < d) p.out_f32[(size_t)bcol * d + n] = v;
-      else if (n < 2 * d) p.kcache[((size_t)bcol * p.n_ctx + pos) * d + (n - d)] = __float2bfloat16(v);
-      else p.vcache[((size_t)bcol * p.n_ctx + pos) * d + (n - 2 * d)] = __float2bfloat16(v);
+      if (n < d) {
+        p.out_f32[(size_t)bcol * d + n] = v;
+      } else {  // KV cache is head-major: [B][n_heads][n_ctx][64]
+        const int c = (n < 2 * d) ? n - d : n - 2 * d;
+        bf16* dst = (n < 2 * d) ? p.kcache : p.vcache;
+        dst[(((size_t)bcol * p.n_heads + (c >> 6)) * p.n_ctx + pos) * 64 + (c & 63)] = __float2bfloat16(v);
+      }
     }
   }
 }
@@ -421,7 +426,7 @@ __device__ __forceinline__ void attend_rows(const float* __restrict__ q64, const
   (void)kMaxN;
 }
 
-// causal self-attention for one new token: grid (n_heads, B); q f32 [B, d] (pre-scaled), caches bf16 [B, n_ctx, d]
+// causal self-attention for one new token: grid (n_heads, B); q f32 [B, d] (pre-scaled), caches bf16 [B, n_heads, n_ctx, 64]
 static constexpr int kSThreads = 128;
 __global__ void __launch_bounds__(kSThreads) self_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kc,
                                                              const bf16* __restrict__ vc, bf16* __restrict__ out,
@@ -433,14 +438,14 @@ __global__ void __launch_bounds__(kSThreads) self_attn_kernel(const float* __res
   const int h = blockIdx.x, b = blockIdx.y;
   pdl_wait();  // pos and the cache row of this step come from the previous kernels
   const int n = st->pos + 1;  // keys 0..pos
-  const bf16* kb = kc + (size_t)b * n_ctx * d + h * 64;
-  const bf16* vb = vc + (size_t)b * n_ctx * d + h * 64;
-  attend_rows<kSThreads, 4, 448, false>(q + (size_t)b * d + h * 64, kb, vb, (size_t)d, n, sq, sp, sred, so,
+  const bf16* kb = kc + ((size_t)b * gridDim.x + h) * n_ctx * 64;
+  const bf16* vb = vc + ((size_t)b * gridDim.x + h) * n_ctx * 64;
+  attend_rows<kSThreads, 4, 448, false>(q + (size_t)b * d + h * 64, kb, vb, (size_t)64, n, sq, sp, sred, so,
                                  out + (size_t)b * d + h * 64, nullptr, st, 0, 0);
 }
 
 // cross-attention for one new token over F encoder frames: grid (n_heads, B)
-// xkv layer slice: bf16 [B, F, 2, n_heads, 64];  q f32 [B, d] (pre-scaled);  out bf16 [B, d]
+// xkv layer slice: bf16 [B, n_heads, 2, F, 64];  q f32 [B, d] (pre-scaled);  out bf16 [B, d]
 // align_out f32 [B, H_a, T_cap, F]: row s = pos - n_prompt of slot align_map[h] gets the probabilities
 static constexpr int kXThreads = 512;
 static constexpr int kFMax = 1500;
@@ -454,9 +459,9 @@ __global__ void __launch_bounds__(kXThreads, 2) cross_attn_kernel(const float* _
   __shared__ float sred[kXThreads / 32];
   __shared__ float so[kXThreads / 8][65];
   const int h = blockIdx.x, b = blockIdx.y;
-  const size_t fstride = (size_t)2 * d;  // elements per frame (K | V)
-  const bf16* kb = xkv + (size_t)b * F * fstride + h * 64;
-  const bf16* vb = kb + d;
+  const size_t fstride = 64;  // head-major: the K rows of (sample, head) are contiguous, then its V rows
+  const bf16* kb = xkv + ((size_t)b * gridDim.x + h) * 2 * F * 64;
+  const bf16* vb = kb + (size_t)F * 64;
   const int slot = align_map_layer[h];
   float* prob_rows = (slot >= 0 && align_out != nullptr) ? align_out + ((size_t)b * H_a + slot) * T_cap * F : nullptr;
   attend_rows<kXThreads, 8, kFMax, true>(q + (size_t)b * d + h * 64, kb, vb, fstride, F, sq, sp, sred, so,
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(SampleParams p) {
   sample_body(p, blockIdx.x, p.st->pos, sh, sh_i, sh_v);
 }
 
-#include "decoder_mega.cuh"
+#include "decoder_stream.cuh"
 
 __global__ void advance_kernel(DecState* st) {
   pdl_trigger();
@@ -714,14 +719,21 @@ struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
   float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg; void* prog;
-  void* xunits; int* xsplits;
+  void* xitems; int* xitem_off; int* xsplits; float* spart;
 };
 
-static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
+static inline int stream_chunk_rows(const ModelDesc& m) { return m.d_model / 16; }   // K|V rows per 16*d-byte ring slot
+static inline int stream_chunks_per_task(const ModelDesc& m) {
+  const int cr = stream_chunk_rows(m);
+  return (m.n_audio_ctx + cr - 1) / cr;
+}
+
+static size_t dec_layout(const ModelDesc& m, int B, int n_cta, DecBuffers* o, void* ws) {
   Arena a(ws ? ws : (void*)nullptr, (size_t)-1);
   char* base = (char*)ws;
   auto take = [&](size_t bytes) -> void* { void* p = a.take(bytes); return base ? p : (void*)nullptr; };
   const size_t d = m.d_model;
+  const size_t tasks = (size_t)B * m.n_heads, cpt = (size_t)stream_chunks_per_task(m);
   DecBuffers t;
   t.x = (float*)take((size_t)B * d * 4);
   t.qbuf = (float*)take((size_t)B * d * 4);
@@ -729,16 +741,18 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
   t.hbuf = (bf16*)take((size_t)B * m.ffn_dim * 2);
   t.xn = (bf16*)take((size_t)B * d * 2);
   t.logits = (float*)take((size_t)B * m.vocab_padded * 4);
-  t.kc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);
+  t.kc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);   // [L][B][H][n_ctx][64]
   t.vc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);
   t.st = (DecState*)take(sizeof(DecState));
   t.finished = (int*)take((size_t)B * 4);
   t.seq = (int*)take((size_t)B * m.n_text_ctx * 4);
-  t.xpart = (float*)take((size_t)B * m.n_heads * kXMaxSplit * 66 * 4);
-  t.xunits = take((size_t)4 * 1024 * sizeof(XUnit));   // up to 1024 CTAs
-  t.xsplits = (int*)take((size_t)B * m.n_heads * 4);
-  t.xscore = (float*)take((size_t)B * m.n_heads * m.n_audio_ctx * 4);
-  t.xcount = (unsigned int*)take((size_t)B * m.n_heads * 4);
+  t.xpart = (float*)take(tasks * cpt * 66 * 4);
+  t.xitems = take((tasks * cpt + 16) * sizeof(XItem));
+  t.xitem_off = (int*)take((size_t)(n_cta + 1) * 4);
+  t.xsplits = (int*)take(tasks * 4);
+  t.xscore = (float*)take(tasks * m.n_audio_ctx * 4);
+  t.xcount = (unsigned int*)take(tasks * 4);
+  t.spart = (float*)take((size_t)2 * B * n_cta * 8 * 4);
   t.bar = (unsigned int*)take(256);
   t.dbg = (unsigned long long*)take(32 * 8);
   t.prog = take((size_t)(8 * m.dec_layers + 4) * 128);
@@ -748,7 +762,7 @@ static size_t dec_layout(const ModelDesc& m, int B, DecBuffers* o, void* ws) {
 
 size_t decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new) {
   (void)max_new;
-  return dec_layout(ctx->md, B, nullptr, nullptr);
+  return dec_layout(ctx->md, B, ctx->sm_count, nullptr, nullptr);
 }
 
 // CW_DEC_PROFILE: one event after every kernel; consecutive differences are per-kernel device times.
@@ -828,7 +842,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
     memset(&g, 0, sizeof(g));
     g.W = (const bf16*)L[CW_DL_WQKV]; g.bias = (const float*)L[CW_DL_BQKV]; g.N = 3 * d; g.K = d; g.B = B;
     g.x_f32 = bf.x; g.ln_g = (const float*)L[CW_DL_LN1_G]; g.ln_b = (const float*)L[CW_DL_LN1_B];
-    g.out_f32 = bf.qbuf; g.kcache = bf.kc + l * cache_l; g.vcache = bf.vc + l * cache_l; g.d = d; g.n_ctx = m.n_text_ctx;
+    g.out_f32 = bf.qbuf; g.kcache = bf.kc + l * cache_l; g.vcache = bf.vc + l * cache_l; g.d = d; g.n_ctx = m.n_text_ctx; g.n_heads = m.n_heads;
     g.st = bf.st;
     if ((rc = gemv(ctx, B, EPI_QKV, g, st)) != CW_OK) return rc;
     CW_CUDA(launch_k(self_attn_kernel, dim3(m.n_heads, B), dim3(kSThreads), 0, st, (const float*)bf.qbuf,
@@ -892,153 +906,247 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
   return CW_OK;
 }
 
-// Measured and rejected on B200 (each was slower than the plain kernel): carrying the first weight batch of
-// the next projection across the grid barrier in registers or in a cp.async smem buffer (2.83 vs 2.44 ms/step), pulling
-// the next phase's operand into L2 with cp.async.bulk.prefetch.L2 (2.69 vs 2.39 ms/step), and issuing a phase's first
-// weight batch before its LayerNorm (2.29 vs 2.26 ms/step). ncu: the warps wait on barriers and dependent loads (stall
-// barrier 11.4, long scoreboard 5.1 per issued instruction); HBM bandwidth and instruction fetch are not the limiters.
-
-// Cross-attention work units: every (sample, head) is cut into 3 or 4 equal frame ranges so that the grid's 4 x #CTA
-// group slots are (nearly) all used, then the ranges are dealt to the CTAs longest-first, each to the CTA that has streamed
-// the fewest frames so far and still has a free slot. With 160 tasks on 148 SMs: 112 tasks x 4 ranges of 375 frames + 48 x 3
-// of 500 = 592 units, 1500..1625 frames per CTA (a fixed 3-way cut gives 36 CTAs 2000 frames and the rest 1500).
-static int plan_cross_units(int tasks, int F, int n_cta, std::vector<XUnit>* units, std::vector<int>* splits) {
-  const int slots = 4 * n_cta;
-  if (3 * tasks > slots || n_cta > 1024) return -1;
-  int n4 = slots - 3 * tasks;
-  if (n4 > tasks) n4 = tasks;
-  if (F % 4 != 0 || F / 4 > kXMaxFrames) n4 = 0;
-  if (F % 3 != 0 || F / 3 > kXMaxFrames) return -1;
-  struct U { int task, split, f0, nf; };
-  std::vector<U> all;
-  splits->assign(tasks, 3);
-  for (int t = 0; t < tasks; ++t) {
-    const int ns = (t < n4) ? 4 : 3;
-    (*splits)[t] = ns;
-    for (int i = 0; i < ns; ++i) all.push_back({t, i, i * (F / ns), F / ns});
-  }
-  std::stable_sort(all.begin(), all.end(), [](const U& a, const U& b) { return a.nf > b.nf; });
-  units->assign((size_t)slots, XUnit{-1, 0, 0, 0});
-  std::vector<int> load(n_cta, 0), used(n_cta, 0);
-  for (const U& u : all) {
-    int best = -1;
-    for (int c = 0; c < n_cta; ++c)
-      if (used[c] < 4 && (best < 0 || load[c] < load[best])) best = c;
-    if (best < 0) return -1;
-    (*units)[(size_t)best * 4 + used[best]] = XUnit{u.task, u.split, u.f0, u.nf};
-    load[best] += u.nf;
-    used[best] += 1;
+// ---------------------------------------------------------------------------------------------------------
+// Streaming step kernel: host side (plan, packing, launch)
+// ---------------------------------------------------------------------------------------------------------
+// Cross-attention plan: every (sample, head) task is cut into chunks of `cr` frames (one ring slot each); the tasks x
+// chunks units are dealt as contiguous ranges to the 4 x n_cta consumer groups, so that every group streams the same
+// number of chunks (+-1) and a CTA walks a contiguous region of the head-major K/V tensor. The part of a task that lands
+// in one group is a segment (its partial softmax is merged by the last arriver). Items of a CTA are emitted in the order
+// the producer issues them: round-robin over its 4 groups.
+static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XItem>* items, std::vector<int>* cta_off,
+                            std::vector<int>* splits) {
+  if (tasks < 1 || F < 1 || cr < 1 || n_cta < 1) return -1;
+  const int cpt = (F + cr - 1) / cr;
+  const long long U = (long long)tasks * cpt, NG = 4LL * n_cta;
+  splits->assign(tasks, 0);
+  items->clear();
+  cta_off->assign((size_t)n_cta + 1, 0);
+  std::vector<XItem> grp[4];
+  for (int c = 0; c < n_cta; ++c) {
+    for (int gi = 0; gi < 4; ++gi) {
+      grp[gi].clear();
+      const long long gg = 4LL * c + gi;
+      const long long u0 = gg * U / NG, u1 = (gg + 1) * U / NG;
+      for (long long u = u0; u < u1; ++u) {
+        const int task = (int)(u / cpt), ch = (int)(u % cpt);
+        XItem it;
+        it.task = task; it.f0 = ch * cr; it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr); it.group = (short)gi;
+        const bool first = (u == u0) || ch == 0, last = (u == u1 - 1) || ch == cpt - 1;
+        if (first) (*splits)[task] += 1;
+        it.seg = (short)((*splits)[task] - 1);
+        it.flags = (short)((first ? 1 : 0) | (last ? 2 : 0));
+        grp[gi].push_back(it);
+      }
+    }
+    size_t mx = 0;
+    for (int gi = 0; gi < 4; ++gi) mx = std::max(mx, grp[gi].size());
+    for (size_t ci = 0; ci < mx; ++ci)
+      for (int gi = 0; gi < 4; ++gi)
+        if (ci < grp[gi].size()) items->push_back(grp[gi][ci]);
+    (*cta_off)[(size_t)c + 1] = (int)items->size();
   }
   return 0;
 }
 
-// host-only view of the plan for tests (cw_decode_cross_plan): units_out [4 * n_cta][4] = {task, split, f0, nf}
-int decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out) {
-  std::vector<XUnit> units;
-  std::vector<int> splits;
-  CW_REQUIRE(tasks >= 1 && n_frames >= 1 && n_cta >= 1 && units_out && splits_out, CW_ERR_INVALID, "cw_decode_cross_plan: bad argument");
-  CW_REQUIRE(plan_cross_units(tasks, n_frames, n_cta, &units, &splits) == 0, CW_ERR_UNSUPPORTED,
-             "cw_decode_cross_plan: %d tasks x %d frames do not fit 4 x %d slots", tasks, n_frames, n_cta);
-  for (size_t i = 0; i < units.size(); ++i) {
-    units_out[4 * i] = units[i].task; units_out[4 * i + 1] = units[i].split;
-    units_out[4 * i + 2] = units[i].f0; units_out[4 * i + 3] = units[i].nf;
+// host-only view of the plan for tests (cw_decode_cross_plan): items_out [tasks * ceil(F/cr)][6] =
+// {task, first frame, frames, group, segment, flags}, cta_off_out [n_cta + 1], splits_out [tasks]
+int decode_cross_plan(int tasks, int n_frames, int chunk_rows, int n_cta, int32_t* items_out, int32_t* cta_off_out,
+                      int32_t* splits_out) {
+  std::vector<XItem> items;
+  std::vector<int> off, splits;
+  CW_REQUIRE(items_out && cta_off_out && splits_out, CW_ERR_INVALID, "cw_decode_cross_plan: NULL argument");
+  CW_REQUIRE(plan_cross_items(tasks, n_frames, chunk_rows, n_cta, &items, &off, &splits) == 0, CW_ERR_INVALID,
+             "cw_decode_cross_plan: bad argument (tasks=%d frames=%d chunk_rows=%d n_cta=%d)", tasks, n_frames, chunk_rows, n_cta);
+  for (size_t i = 0; i < items.size(); ++i) {
+    items_out[6 * i] = items[i].task; items_out[6 * i + 1] = items[i].f0; items_out[6 * i + 2] = items[i].nf;
+    items_out[6 * i + 3] = items[i].group; items_out[6 * i + 4] = items[i].seg; items_out[6 * i + 5] = items[i].flags;
   }
+  for (size_t i = 0; i < off.size(); ++i) cta_off_out[i] = off[i];
   for (int t = 0; t < tasks; ++t) splits_out[t] = splits[t];
   return CW_OK;
 }
 
-// fill the step parameters of the persistent kernel and upload them to constant memory (once per decode call)
-static int mega_upload_params(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int B, int n_prompt, int max_new, int flags,
-                              const int* forced, float* align_out, float* logits_out, int* argmax_out, cudaStream_t st) {
-  const ModelDesc& m = ctx->md;
-  MegaParams p;
-  memset(&p, 0, sizeof(p));
-  p.W = (const void* const*)ctx->d_w;
-  p.enc_layers = m.enc_layers; p.dec_layers = m.dec_layers; p.d = m.d_model; p.n_heads = m.n_heads; p.ffn = m.ffn_dim;
-  p.Vp = m.vocab_padded; p.n_ctx = m.n_text_ctx; p.F = m.n_audio_ctx; p.B = B;
-  p.x = bf.x; p.qbuf = bf.qbuf; p.attn = bf.attn; p.hbuf = bf.hbuf; p.logits = bf.logits; p.kc = bf.kc; p.vc = bf.vc;
-  p.st = bf.st; p.seq = bf.seq; p.xkv = xkv; p.align_map = ctx->d_align_map; p.align_out = align_out;
-  p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
-  p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.bar = bf.bar;
-  {
-    std::vector<XUnit> units;
-    std::vector<int> splits;
-    CW_REQUIRE(plan_cross_units(B * m.n_heads, m.n_audio_ctx, ctx->sm_count, &units, &splits) == 0, CW_ERR_UNSUPPORTED,
-               "decode megakernel: cannot lay out %d cross-attention tasks on %d CTAs", B * m.n_heads, ctx->sm_count);
-    CW_CUDA(cudaMemcpyAsync(bf.xunits, units.data(), units.size() * sizeof(XUnit), cudaMemcpyHostToDevice, st));
-    CW_CUDA(cudaMemcpyAsync(bf.xsplits, splits.data(), splits.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CW_CUDA(cudaStreamSynchronize(st));  // the vectors die at the end of this block
-    p.xunits = (const XUnit*)bf.xunits;
-    p.xsplits = bf.xsplits;
+// ---- fragment-major copies of the decoder matrices (cw_decode_pack) ----
+struct PackTab {  // element offsets inside the pack buffer
+  std::vector<size_t> off;   // [dec_layers][6] then tok_emb
+  size_t total;
+};
+static const int kPackSlots[6] = {CW_DL_WQKV, CW_DL_WO, CW_DL_WQC, CW_DL_WOC, CW_DL_W1, CW_DL_W2};
+static void pack_dims(const ModelDesc& m, int which, int* N, int* K) {
+  const int d = m.d_model;
+  switch (which) {
+    case 0: *N = 3 * d; *K = d; break;
+    case 4: *N = m.ffn_dim; *K = d; break;
+    case 5: *N = d; *K = m.ffn_dim; break;
+    default: *N = d; *K = d; break;
   }
-  p.dbg = getenv("CW_MEGA_DEBUG") ? bf.dbg : nullptr;
-  SampleParams& sp = p.sp;
-  sp.logits = bf.logits; sp.suppress = ctx->d_suppress; sp.seq = bf.seq; sp.seq_ld = m.n_text_ctx;
-  sp.finished = bf.finished; sp.st = bf.st; sp.V = m.vocab; sp.Vp = m.vocab_padded; sp.n_prompt = n_prompt;
-  sp.max_new = max_new; sp.eos = m.eos_id; sp.no_ts = m.no_timestamps_id; sp.max_initial_ts = m.max_initial_timestamp_index;
-  sp.flags = flags; sp.forced = forced; sp.logits_out = logits_out; sp.argmax_out = argmax_out;
-  // the step as a program of phases
-  static_assert(sizeof(PhaseDesc) <= 128, "PhaseDesc grew beyond its workspace slot");
-  std::vector<PhaseDesc> prog;
-  auto gemv_ph = [&](int slot, int epi, int kmax, int N, int K, const void* Wm, const void* bias, const void* g, const void* bt,
-                     const float* src_f32, const bf16* src_bf16, float* out_f32, bf16* out_bf16, bf16* kcp, bf16* vcp) {
-    PhaseDesc d;
-    memset(&d, 0, sizeof(d));
-    d.type = PH_GEMV; d.epi = epi; d.kmax = kmax; d.N = N; d.K = K; d.ln = (g != nullptr); d.dbg_slot = slot;
-    d.W = (const bf16*)Wm; d.bias = (const float*)bias; d.ln_g = (const float*)g; d.ln_b = (const float*)bt;
-    d.src_f32 = src_f32; d.src_bf16 = src_bf16; d.out_f32 = out_f32; d.out_bf16 = out_bf16; d.kcache = kcp; d.vcache = vcp;
-    prog.push_back(d);
+}
+static PackTab pack_table(const ModelDesc& m) {
+  PackTab t;
+  size_t o = 0;
+  for (int l = 0; l < m.dec_layers; ++l)
+    for (int w = 0; w < 6; ++w) {
+      int N, K;
+      pack_dims(m, w, &N, &K);
+      t.off.push_back(o);
+      o += align_up((size_t)N * K, 128);
+    }
+  t.off.push_back(o);
+  o += align_up((size_t)m.vocab_padded * m.d_model, 128);
+  t.total = o;
+  return t;
+}
+
+size_t decode_pack_bytes(const cw_ctx* ctx) { return pack_table(ctx->md).total * sizeof(bf16); }
+
+int decode_pack_run(cw_ctx* ctx, void* buf, size_t bytes, cudaStream_t st) {
+  const ModelDesc& m = ctx->md;
+  const PackTab t = pack_table(m);
+  CW_REQUIRE(buf && bytes >= t.total * sizeof(bf16), CW_ERR_WORKSPACE, "cw_decode_pack: buffer %zu < %zu", bytes,
+             t.total * sizeof(bf16));
+  CW_REQUIRE(((uintptr_t)buf & 127) == 0, CW_ERR_INVALID, "cw_decode_pack: buffer must be 128-byte aligned");
+  CW_REQUIRE(m.d_model % 16 == 0 && m.ffn_dim % 16 == 0, CW_ERR_UNSUPPORTED, "cw_decode_pack: dims must be multiples of 16");
+  bf16* out = (bf16*)buf;
+  auto run = [&](const void* W, size_t off, int N, int K) -> int {
+    const size_t pieces = (size_t)N * K / 8;
+    const int grid = (int)std::min<size_t>((pieces + 255) / 256, 4096);
+    pack_frag_kernel<<<grid, 256, 0, st>>>((const bf16*)W, out + off, N, K);
+    CW_CHECK_LAUNCH("pack_frag_kernel");
+    ctx->launches += 1;
+    return CW_OK;
   };
-  auto simple_ph = [&](int type, int slot, int l) {
-    PhaseDesc d;
-    memset(&d, 0, sizeof(d));
-    d.type = type; d.l = l; d.dbg_slot = slot;
-    prog.push_back(d);
-  };
-  const int d_ = m.d_model;
-  const size_t cache_l = (size_t)B * m.n_text_ctx * d_;
-  simple_ph(PH_EMBED, 0, 0);
+  int rc;
   for (int l = 0; l < m.dec_layers; ++l) {
     const void** Lw = ctx->w + CW_W_GLOBAL_COUNT + (size_t)m.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
-    gemv_ph(1, EPI_QKV, 8, 3 * d_, d_, Lw[CW_DL_WQKV], Lw[CW_DL_BQKV], Lw[CW_DL_LN1_G], Lw[CW_DL_LN1_B], bf.x, nullptr, bf.qbuf, nullptr,
-            bf.kc + l * cache_l, bf.vc + l * cache_l);
-    simple_ph(PH_SELF_ATTN, 2, l);
-    gemv_ph(3, EPI_RESID, 8, d_, d_, Lw[CW_DL_WO], Lw[CW_DL_BO], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
-    gemv_ph(4, EPI_F32, 8, d_, d_, Lw[CW_DL_WQC], Lw[CW_DL_BQC], Lw[CW_DL_LN2_G], Lw[CW_DL_LN2_B], bf.x, nullptr, bf.qbuf, nullptr, nullptr, nullptr);
-    simple_ph(PH_CROSS_ATTN, 5, l);
-    gemv_ph(6, EPI_RESID, 8, d_, d_, Lw[CW_DL_WOC], Lw[CW_DL_BOC], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
-    gemv_ph(7, EPI_GELU_BF16, 4, m.ffn_dim, d_, Lw[CW_DL_W1], Lw[CW_DL_B1], Lw[CW_DL_LN3_G], Lw[CW_DL_LN3_B], bf.x, nullptr, nullptr, bf.hbuf, nullptr, nullptr);
-    gemv_ph(8, EPI_RESID, 16, d_, m.ffn_dim, Lw[CW_DL_W2], Lw[CW_DL_B2], nullptr, nullptr, nullptr, bf.hbuf, bf.x, nullptr, nullptr, nullptr);
+    for (int w = 0; w < 6; ++w) {
+      int N, K;
+      pack_dims(m, w, &N, &K);
+      if ((rc = run(Lw[kPackSlots[w]], t.off[(size_t)l * 6 + w], N, K)) != CW_OK) return rc;
+    }
   }
-  gemv_ph(9, EPI_F32, 4, m.vocab_padded, d_, ctx->w[CW_W_TOK_EMB], nullptr, ctx->w[CW_W_DEC_LNF_G], ctx->w[CW_W_DEC_LNF_B], bf.x, nullptr,
-          bf.logits, nullptr, nullptr, nullptr);
-  CW_REQUIRE(prog.size() <= (size_t)(8 * m.dec_layers + 4), CW_ERR_INVALID, "decode program too long");
-  CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice, st));
-  p.prog = (const PhaseDesc*)bf.prog;
-  p.n_phases = (int)prog.size();
-  CW_CUDA(cudaMemcpyToSymbolAsync(c_mp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
-  CW_CUDA(cudaStreamSynchronize(st));  // `p` is a stack object
+  if ((rc = run(ctx->w[CW_W_TOK_EMB], t.off.back(), m.vocab_padded, m.d_model)) != CW_OK) return rc;
+  ctx->pack_buf = buf;
   return CW_OK;
 }
 
-// one cooperative launch for the whole step
-static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
+struct StreamCfg { int NS, ns_log, SB, CR, TB, XR, xs_off, red_off; size_t smem; };
+
+static bool stream_config(const ModelDesc& m, int B, StreamCfg* c) {
+  const int d = m.d_model;
+  if (d % 128 != 0 || d > 16 * 16 * kSKsMax || m.ffn_dim % d != 0 || B > 16 || m.n_text_ctx > 448) return false;
+  c->SB = 16 * d; c->CR = d / 16; c->XR = (B > 8) ? 16 : 8;
+  const size_t xs_bytes = align_up((size_t)c->XR * (d + 16) * 2, 128);
+  const size_t limit = 227 * 1024 - 1024;   // static smem (barriers, flags) + slack
+  for (int ns = kSMaxSlots; ns >= 2; ns >>= 1)
+    for (int tb = 4; tb >= 2; tb >>= 1) {
+      const size_t red_bytes = (size_t)16 * tb * 128 * 4;
+      const size_t total = (size_t)ns * c->SB + xs_bytes + red_bytes;
+      if (total <= limit && xs_bytes + red_bytes >= (size_t)4 * kSGroupFloats * 4) {
+        c->NS = ns; c->TB = tb; c->ns_log = 0;
+        while ((1 << c->ns_log) < ns) c->ns_log += 1;
+        c->xs_off = ns * c->SB; c->red_off = c->xs_off + (int)xs_bytes; c->smem = total;
+        return true;
+      }
+    }
+  return false;
+}
+
+// fill the step parameters of the streaming kernel and upload them to constant memory (once per decode call)
+static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamCfg& sc, const bf16* xkv, int B, int n_prompt,
+                                int max_new, int flags, const int* forced, float* align_out, float* logits_out, int* argmax_out,
+                                cudaStream_t st) {
   const ModelDesc& m = ctx->md;
-  const size_t smem_gemv = (size_t)8 * (m.d_model + 32) * 2 + (size_t)2 * m.d_model * 4 + (size_t)kMegaWarps * 128 * 4;
-  // attention phases alias the same buffer: 4 groups x 8 KB scratch + the cross-attention K/V rings
-  const size_t smem_attn = (size_t)4 * 2048 * 4 + (size_t)4 * kXRing * 2 * 128 * 16;
-  const size_t smem = smem_gemv > smem_attn ? smem_gemv : smem_attn;
-  CW_REQUIRE(smem <= 227 * 1024, CW_ERR_UNSUPPORTED, "decode megakernel: smem %zu too large", smem);
-  CW_REQUIRE(m.n_text_ctx <= 1024, CW_ERR_UNSUPPORTED, "decode megakernel: context too long");
-  CW_CUDA(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int G = ctx->sm_count;
+  StreamParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = m.d_model; p.n_heads = m.n_heads; p.n_ctx = m.n_text_ctx; p.F = m.n_audio_ctx; p.B = B; p.Vp = m.vocab_padded;
+  p.V = m.vocab; p.dec_layers = m.dec_layers;
+  p.G = G; p.NS = sc.NS; p.ns_log = sc.ns_log; p.SB = sc.SB; p.CR = sc.CR; p.TB = sc.TB; p.XR = sc.XR;
+  p.xs_off = sc.xs_off; p.red_off = sc.red_off;
+  p.x = bf.x; p.qbuf = bf.qbuf; p.attn = bf.attn; p.hbuf = bf.hbuf; p.kc = bf.kc; p.vc = bf.vc;
+  p.st = bf.st; p.seq = bf.seq; p.finished = bf.finished; p.xkv = xkv;
+  p.tok_emb = (const bf16*)ctx->w[CW_W_TOK_EMB]; p.dec_pos = (const float*)ctx->w[CW_W_DEC_POS];
+  p.align_map = ctx->d_align_map; p.align_out = align_out; p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
+  p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.xsplits = bf.xsplits;
+  p.part_stride = stream_chunks_per_task(m);
+  p.bar = bf.bar; p.spart = bf.spart;
+  p.dbg = getenv("CW_MEGA_DEBUG") ? bf.dbg : nullptr;
+  p.suppress = ctx->d_suppress; p.max_new = max_new; p.eos = m.eos_id; p.no_ts = m.no_timestamps_id;
+  p.max_initial_ts = m.max_initial_timestamp_index; p.flags = flags;
+  p.forced = forced; p.logits_out = logits_out; p.argmax_out = argmax_out;
+  {
+    std::vector<XItem> items;
+    std::vector<int> off, splits;
+    CW_REQUIRE(plan_cross_items(B * m.n_heads, m.n_audio_ctx, sc.CR, G, &items, &off, &splits) == 0, CW_ERR_UNSUPPORTED,
+               "decode step kernel: cannot lay out %d cross-attention tasks on %d CTAs", B * m.n_heads, G);
+    CW_CUDA(cudaMemcpyAsync(bf.xitems, items.data(), items.size() * sizeof(XItem), cudaMemcpyHostToDevice, st));
+    CW_CUDA(cudaMemcpyAsync(bf.xitem_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CW_CUDA(cudaMemcpyAsync(bf.xsplits, splits.data(), splits.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CW_CUDA(cudaStreamSynchronize(st));  // the vectors die at the end of this block
+    p.xitems = (const XItem*)bf.xitems;
+    p.xitem_off = bf.xitem_off;
+  }
+  // the step as a program of phases
+  static_assert(sizeof(SPhase) <= 128, "SPhase grew beyond its workspace slot");
+  const PackTab pt = pack_table(m);
+  const bf16* pk = (const bf16*)ctx->pack_buf;
+  std::vector<SPhase> prog;
+  int rot = 0;
+  auto gemv_ph = [&](int slot, int epi, int N, int K, const bf16* Wp, const void* bias, const void* g, const void* bt,
+                     const float* src_f32, const bf16* src_bf16, float* out_f32, bf16* out_bf16, bf16* kcp, bf16* vcp) {
+    SPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.type = SPH_GEMV; ph.epi = epi; ph.N = N; ph.K = K; ph.ln = (g != nullptr); ph.dbg_slot = slot; ph.rot = rot;
+    ph.Wp = Wp; ph.bias = (const float*)bias; ph.ln_g = (const float*)g; ph.ln_b = (const float*)bt;
+    ph.src_f32 = src_f32; ph.src_bf16 = src_bf16; ph.out_f32 = out_f32; ph.out_bf16 = out_bf16; ph.kcache = kcp; ph.vcache = vcp;
+    prog.push_back(ph);
+    rot = (rot + G - (N / 8) % G) % G;   // the CTAs that got the remainder tiles of this phase are not the next phase's
+  };
+  auto simple_ph = [&](int type, int slot, int l) {
+    SPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.type = type; ph.l = l; ph.dbg_slot = slot;
+    prog.push_back(ph);
+  };
+  const int d_ = m.d_model;
+  const size_t cache_l = (size_t)B * m.n_text_ctx * d_;
+  simple_ph(SPH_SAMPLE_EMBED, 0, 0);
+  for (int l = 0; l < m.dec_layers; ++l) {
+    const void** Lw = ctx->w + CW_W_GLOBAL_COUNT + (size_t)m.enc_layers * CW_EL_COUNT + (size_t)l * CW_DL_COUNT;
+    const size_t* po = &pt.off[(size_t)l * 6];
+    gemv_ph(1, EPI_QKV, 3 * d_, d_, pk + po[0], Lw[CW_DL_BQKV], Lw[CW_DL_LN1_G], Lw[CW_DL_LN1_B], bf.x, nullptr, bf.qbuf, nullptr,
+            bf.kc + l * cache_l, bf.vc + l * cache_l);
+    simple_ph(SPH_SELF, 2, l);
+    gemv_ph(3, EPI_RESID, d_, d_, pk + po[1], Lw[CW_DL_BO], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
+    gemv_ph(4, EPI_F32, d_, d_, pk + po[2], Lw[CW_DL_BQC], Lw[CW_DL_LN2_G], Lw[CW_DL_LN2_B], bf.x, nullptr, bf.qbuf, nullptr, nullptr, nullptr);
+    simple_ph(SPH_CROSS, 5, l);
+    gemv_ph(6, EPI_RESID, d_, d_, pk + po[3], Lw[CW_DL_BOC], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
+    gemv_ph(7, EPI_GELU_BF16, m.ffn_dim, d_, pk + po[4], Lw[CW_DL_B1], Lw[CW_DL_LN3_G], Lw[CW_DL_LN3_B], bf.x, nullptr, nullptr, bf.hbuf, nullptr, nullptr);
+    gemv_ph(8, EPI_RESID, d_, m.ffn_dim, pk + po[5], Lw[CW_DL_B2], nullptr, nullptr, nullptr, bf.hbuf, bf.x, nullptr, nullptr, nullptr);
+  }
+  gemv_ph(9, EPI_LOGITS, m.vocab_padded, d_, pk + pt.off.back(), nullptr, ctx->w[CW_W_DEC_LNF_G], ctx->w[CW_W_DEC_LNF_B], bf.x, nullptr,
+          nullptr, nullptr, nullptr, nullptr);
+  CW_REQUIRE(prog.size() <= (size_t)(8 * m.dec_layers + 4), CW_ERR_INVALID, "decode program too long");
+  CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(SPhase), cudaMemcpyHostToDevice, st));
+  p.prog = (const SPhase*)bf.prog;
+  p.n_phases = (int)prog.size();
+  CW_CUDA(cudaMemcpyToSymbolAsync(c_sp, &p, sizeof(p), 0, cudaMemcpyHostToDevice, st));
+  CW_CUDA(cudaStreamSynchronize(st));  // `p` and `prog` are stack objects
+  return CW_OK;
+}
+
+// one cooperative launch for n_steps steps
+static int launch_stream(cw_ctx* ctx, const StreamCfg& sc, int n_steps, int tail_sample, cudaStream_t st) {
+  CW_CUDA(cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc.smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ctx->sm_count); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(ctx->sm_count); cfg.blockDim = dim3(kSAllThreads); cfg.dynamicSmemBytes = sc.smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CW_CUDA(cudaLaunchKernelEx(&cfg, decode_mega_kernel));
+  CW_CUDA(cudaLaunchKernelEx(&cfg, decode_stream_kernel, n_steps, tail_sample));
   ctx->launches += 1;
   return CW_OK;
 }
@@ -1046,7 +1154,7 @@ static int enqueue_step_mega(cw_ctx* ctx, cudaStream_t st) {
 __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
                                 int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { st->pos = 0; st->n_finished = 0; *bar = 0u; }
+  if (i == 0) { st->pos = 0; st->n_finished = 0; st->bar_epoch = 0u; *bar = 0u; }
   if (i < 32) dbg[i] = 0ull;
   if (i < n_xcount) xcount[i] = 0u;
   if (i < B) finished[i] = 0;
@@ -1083,7 +1191,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   size_t need = decode_workspace_bytes(ctx, B, max_new);
   CW_REQUIRE(ws && ws_bytes >= need, CW_ERR_WORKSPACE, "cw_decode_greedy: workspace %zu < %zu", ws_bytes, need);
   DecBuffers bf;
-  dec_layout(m, B, &bf, ws);
+  dec_layout(m, B, ctx->sm_count, &bf, ws);
 
   int n_init = B * m.n_text_ctx;
   dec_init_kernel<<<(n_init + 255) / 256, 256, 0, st>>>(bf.st, bf.finished, bf.seq, m.n_text_ctx, prompt, n_prompt, B,
@@ -1092,88 +1200,109 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
   ctx->launches += 1;
 
   const int total_steps = n_prompt - 1 + max_new;  // positions 0 .. n_prompt+max_new-2
-  // stream capture is not available on the legacy / per-thread default streams
   g_use_pdl = !(flags & CW_DEC_NO_PDL);
   const bool profile = (flags & CW_DEC_PROFILE) != 0;
-  // B <= 8: the whole step is one persistent cooperative kernel; otherwise (or on request) one kernel per operator
-  const bool use_mega = (B <= 8) && (m.d_model <= 1280) && (3 * B * m.n_heads <= 4 * ctx->sm_count) && (ctx->sm_count <= 1024) &&
-                        (m.n_audio_ctx % 3 == 0) && !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
-  auto step_fn = [&](cw_ctx* c) -> int {
-    if (use_mega) return enqueue_step_mega(c, st);
-    return enqueue_step(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
-  };
-  StepProf prof;
-  prof.on = profile; prof.st = st;
-  if (profile) { for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; } }
-  const bool use_graph = !(flags & (CW_DEC_NO_GRAPH | CW_DEC_PROFILE)) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
-  int rc = CW_OK;
-  DecGraph* G = (DecGraph*)ctx->dec_state;
-  if (use_graph) {
-    bool hit = G && G->valid && G->xkv == xkv && G->ws == ws && G->B == B && G->n_prompt == n_prompt &&
-               G->max_new == max_new && G->flags == flags && G->forced == forced && G->align_out == align_out &&
-               G->logits_out == logits_out && G->argmax_out == argmax_out;
-    if (!hit) {
-      if (!G) { G = new DecGraph(); G->valid = false; ctx->dec_state = G; }
-      if (G->valid) { cudaGraphExecDestroy(G->exec); G->valid = false; }
-      // every kernel attribute must be set before capture: run one un-captured "dry" configuration pass is not
-      // needed because cudaFuncSetAttribute is legal during capture (it is not a stream operation).
-      cudaGraph_t graph;
-      long long launches_before = ctx->launches;
-      CW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      rc = step_fn(ctx);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      ctx->launches = launches_before;  // capture does not execute anything
-      if (rc != CW_OK) { if (ce == cudaSuccess && graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
-      ce = cudaGraphInstantiate(&G->exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
-      G->valid = true;
-      G->xkv = xkv; G->ws = ws; G->B = B; G->n_prompt = n_prompt; G->max_new = max_new; G->flags = flags;
-      G->forced = forced; G->align_out = align_out; G->logits_out = logits_out; G->argmax_out = argmax_out;
-    }
-  }
-  const long long per_step = use_mega ? 1 : 5 + 8LL * m.dec_layers;  // kernels in one step
-  if (use_mega) {
-    rc = mega_upload_params(ctx, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
-    if (rc != CW_OK) return rc;
-  }
+  const bool want_stream = !(flags & (CW_DEC_NO_MEGA | CW_DEC_PROFILE));
   int steps_done = 0;  // generated tokens
   int h_state[4] = {0, 0, 0, 0};
-  if (profile) {
-    long long ns = (long long)total_steps * 3000000LL;  // ~3 ms of head start per step for the host
-    if (ns > 400000000LL) ns = 400000000LL;
-    spin_kernel<<<1, 1, 0, st>>>(ns);
-    CW_CHECK_LAUNCH("spin_kernel");
-  }
-  for (int s = 0; s < total_steps; ++s) {
-    if (use_graph) {
-      CW_CUDA(cudaGraphLaunch(G->exec, st));
-      ctx->launches += per_step;
-    } else {
-      if (profile) { g_prof = &prof; prof.mark(3); }
-      rc = step_fn(ctx);
-      g_prof = nullptr;
-      if (rc != CW_OK) return rc;
+  const bool may_stop = !(flags & CW_DEC_SUPPRESS_EOS) && forced == nullptr;
+
+  if (want_stream) {
+    // ---- default: the streaming step kernel (one cooperative launch per kStepsPerLaunch positions) ----
+    StreamCfg sc;
+    CW_REQUIRE(stream_config(m, B, &sc), CW_ERR_UNSUPPORTED,
+               "cw_decode_greedy: the step kernel does not support d_model=%d ffn=%d B=%d (use CW_DEC_NO_MEGA)", m.d_model,
+               m.ffn_dim, B);
+    CW_REQUIRE(ctx->pack_buf != nullptr, CW_ERR_STATE, "cw_decode_greedy: call cw_decode_pack after cw_load_weights");
+    int rc = stream_upload_params(ctx, bf, sc, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out,
+                                  argmax_out, st);
+    if (rc != CW_OK) return rc;
+    int spl = 16;
+    if (const char* e = getenv("CW_STREAM_STEPS")) { spl = atoi(e); if (spl < 1) spl = 1; }
+    int s = 0;
+    bool stopped = false;
+    while (s < total_steps) {
+      const int n = (total_steps - s < spl) ? total_steps - s : spl;
+      const int tail = (s + n == total_steps) ? 1 : 0;
+      if ((rc = launch_stream(ctx, sc, n, tail, st)) != CW_OK) return rc;
+      s += n;
+      if (may_stop && !tail) {
+        CW_CUDA(cudaMemcpyAsync(h_state, bf.st, sizeof(DecState), cudaMemcpyDeviceToHost, st));
+        CW_CUDA(cudaStreamSynchronize(st));
+        if (h_state[1] >= B) { stopped = true; break; }
+      }
     }
-    if (s >= n_prompt - 1) steps_done = s - (n_prompt - 1) + 1;
-    const bool poll = !(flags & CW_DEC_SUPPRESS_EOS) && forced == nullptr && ((s & 15) == 15);
-    if (poll) {
-      CW_CUDA(cudaMemcpyAsync(h_state, bf.st, sizeof(DecState), cudaMemcpyDeviceToHost, st));
+    // tokens exist for positions < s (the token of position s is sampled by the next launch / the tail)
+    steps_done = stopped ? std::max(0, s - n_prompt) : max_new;
+    if (getenv("CW_MEGA_DEBUG")) {
+      unsigned long long h[32];
       CW_CUDA(cudaStreamSynchronize(st));
-      if (h_state[1] >= B) break;
+      CW_CUDA(cudaMemcpy(h, bf.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+      static const char* nm[] = {"sample+emb", "qkv", "self_attn", "o_proj", "q_cross", "cross_attn", "oc_proj", "fc1", "fc2", "logits"};
+      fprintf(stderr, "[CW_MEGA_DEBUG] CTA1 ns per step (compute / barrier wait), %d steps\n", s);
+      for (int i = 0; i < 10; ++i)
+        fprintf(stderr, "  %-10s %9.0f / %9.0f\n", nm[i], (double)h[2 * i] / s, (double)h[2 * i + 1] / s);
     }
-  }
-  if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
-  if (use_mega && getenv("CW_MEGA_DEBUG")) {
-    unsigned long long h[32];
-    CW_CUDA(cudaStreamSynchronize(st));
-    CW_CUDA(cudaMemcpy(h, bf.dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    static const char* nm[] = {"embed", "qkv", "self_attn", "o_proj", "q_cross", "cross_attn", "oc_proj", "fc1", "fc2", "logits"};
-    fprintf(stderr, "[CW_MEGA_DEBUG] CTA0 ns per step (compute / barrier wait), %d steps\n", total_steps);
-    for (int i = 0; i < 10; ++i)
-      fprintf(stderr, "  %-10s %9.0f / %9.0f\n", nm[i], (double)h[2 * i] / total_steps, (double)h[2 * i + 1] / total_steps);
-    fprintf(stderr, "  %-10s %9.0f\n", "sample", (double)h[20] / total_steps);
+  } else {
+    // ---- one kernel per operator (cross-check of the step kernel, CW_DEC_PROFILE) ----
+    StepProf prof;
+    prof.on = profile; prof.st = st;
+    if (profile) { for (int i = 0; i < 4; ++i) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; } }
+    auto step_fn = [&](cw_ctx* c) -> int {
+      return enqueue_step(c, bf, (const bf16*)xkv, B, n_prompt, max_new, flags, forced, align_out, logits_out, argmax_out, st);
+    };
+    // stream capture is not available on the legacy / per-thread default streams
+    const bool use_graph = !(flags & (CW_DEC_NO_GRAPH | CW_DEC_PROFILE)) && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    int rc = CW_OK;
+    DecGraph* G = (DecGraph*)ctx->dec_state;
+    if (use_graph) {
+      bool hit = G && G->valid && G->xkv == xkv && G->ws == ws && G->B == B && G->n_prompt == n_prompt &&
+                 G->max_new == max_new && G->flags == flags && G->forced == forced && G->align_out == align_out &&
+                 G->logits_out == logits_out && G->argmax_out == argmax_out;
+      if (!hit) {
+        if (!G) { G = new DecGraph(); G->valid = false; ctx->dec_state = G; }
+        if (G->valid) { cudaGraphExecDestroy(G->exec); G->valid = false; }
+        cudaGraph_t graph;
+        long long launches_before = ctx->launches;
+        CW_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = step_fn(ctx);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        ctx->launches = launches_before;  // capture does not execute anything
+        if (rc != CW_OK) { if (ce == cudaSuccess && graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        ce = cudaGraphInstantiate(&G->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+        G->valid = true;
+        G->xkv = xkv; G->ws = ws; G->B = B; G->n_prompt = n_prompt; G->max_new = max_new; G->flags = flags;
+        G->forced = forced; G->align_out = align_out; G->logits_out = logits_out; G->argmax_out = argmax_out;
+      }
+    }
+    const long long per_step = 5 + 8LL * m.dec_layers;  // kernels in one step
+    if (profile) {
+      long long ns = (long long)total_steps * 3000000LL;  // ~3 ms of head start per step for the host
+      if (ns > 400000000LL) ns = 400000000LL;
+      spin_kernel<<<1, 1, 0, st>>>(ns);
+      CW_CHECK_LAUNCH("spin_kernel");
+    }
+    for (int s = 0; s < total_steps; ++s) {
+      if (use_graph) {
+        CW_CUDA(cudaGraphLaunch(G->exec, st));
+        ctx->launches += per_step;
+      } else {
+        if (profile) { g_prof = &prof; prof.mark(3); }
+        rc = step_fn(ctx);
+        g_prof = nullptr;
+        if (rc != CW_OK) return rc;
+      }
+      if (s >= n_prompt - 1) steps_done = s - (n_prompt - 1) + 1;
+      if (may_stop && ((s & 15) == 15)) {
+        CW_CUDA(cudaMemcpyAsync(h_state, bf.st, sizeof(DecState), cudaMemcpyDeviceToHost, st));
+        CW_CUDA(cudaStreamSynchronize(st));
+        if (h_state[1] >= B) break;
+      }
+    }
+    if (profile) { CW_CUDA(cudaStreamSynchronize(st)); prof.flush(ctx); }
   }
   dec_finish_kernel<<<B, 128, 0, st>>>(bf.seq, m.n_text_ctx, n_prompt, n_prompt + max_new, m.eos_id, tokens_out, len_out, B,
                                        steps_done);

@@ -360,11 +360,12 @@ int encode_run(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xk
   }
   rc = layernorm_run(ctx, x, (const float*)W[CW_W_ENC_LNF_G], (const float*)W[CW_W_ENC_LNF_B], eo, M, d, st);
   if (rc != CW_OK) return rc;
-  // cross-attention K/V of all decoder layers in one GEMM: N = dec_layers * 2d, stored per layer
+  // cross-attention K/V of all decoder layers in one GEMM: N = dec_layers * 2d, stored head-major so that the decode
+  // step kernel streams every (layer, sample, head) K block and V block as contiguous bulk copies
   memset(&p, 0, sizeof(p));
   p.batch = 1; p.M = M; p.N = m.dec_layers * 2 * d; p.K = d;
   p.bias = (const float*)W[CW_W_XKV_B]; p.C = xkv_out; p.ldc = 2 * d;
-  p.c_split_n = 2 * d; p.c_split_stride = (long long)M * 2 * d; p.out_f32 = 0;
+  p.hm_rows = S; p.hm_heads = m.n_heads; p.hm_batch = B; p.out_f32 = 0;   // head-major: [layer][sample][head][k|v][frame][64]
   rc = gemm_launch(ctx, eo, d, 0, W[CW_W_XKV_W], p, st);
   return rc;
 }

@@ -271,14 +271,24 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               }
             }
           }
-          size_t col_off;
-          if (p.c_split_n > 0) {
-            int g = n0 / p.c_split_n;
-            col_off = (size_t)g * p.c_split_stride + (size_t)(n0 - g * p.c_split_n);
+          size_t off;
+          if (p.hm_rows > 0) {
+            // the 32 columns of this thread lie inside one (layer, k|v, head): 64 contiguous bytes of that head's row
+            const int dm = p.hm_heads * 64;
+            const int layer = n0 / (2 * dm), c = n0 - layer * 2 * dm;
+            const int kv = c / dm, hh = (c - kv * dm) >> 6, e = c & 63;
+            const int smp = m / p.hm_rows, fr = m - smp * p.hm_rows;
+            off = (((((size_t)layer * p.hm_batch + smp) * p.hm_heads + hh) * 2 + kv) * p.hm_rows + fr) * 64 + e;
           } else {
-            col_off = (size_t)n0;
+            size_t col_off;
+            if (p.c_split_n > 0) {
+              int g = n0 / p.c_split_n;
+              col_off = (size_t)g * p.c_split_stride + (size_t)(n0 - g * p.c_split_n);
+            } else {
+              col_off = (size_t)n0;
+            }
+            off = (size_t)b * p.c_bs + (size_t)m * p.ldc + col_off;
           }
-          const size_t off = (size_t)b * p.c_bs + (size_t)m * p.ldc + col_off;
           if (p.out_f32) {
             float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
 #pragma unroll

@@ -19,6 +19,9 @@ struct GemmParams {
   int ldc;
   int c_split_n;       // 0, or: columns are stored in groups of c_split_n, group g at C + g*c_split_stride
   long long c_split_stride;
+  int hm_rows;         // > 0: head-major K/V store — row m = (sample, frame) with hm_rows frames per sample, column n =
+                       // (layer, k|v, head, 64): element goes to C[layer][sample][head][k|v][frame][64]  (hm_heads heads, hm_batch samples)
+  int hm_heads, hm_batch;
   int gelu, out_f32;
 };
 

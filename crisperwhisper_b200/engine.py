@@ -111,6 +111,12 @@ class Engine:
             L.check(self.lib.cw_load_weights(self._h, ptrs, len(packed.tensors), C.byref(d)), "cw_load_weights")
         self.weights = packed  # keep the tensors alive: the library borrows the pointers
         self.desc = c
+        # fragment-major copies of the decoder matrices for the streaming step kernel (caller-owned, like the weights)
+        nb = int(self.lib.cw_decode_pack_bytes(self._h))
+        with self._on_stream():
+            self._pack = torch.empty(nb, dtype=torch.uint8, device=self.device)
+            L.check(self.lib.cw_decode_pack(self._h, _p(self._pack), nb, self._sp()), "cw_decode_pack")
+        self.stream.synchronize()
 
     # -- stage 1 -----------------------------------------------------------------------------------------
     def logmel(self, wave: torch.Tensor, mel_filters: torch.Tensor, n_valid: Optional[torch.Tensor] = None,
@@ -153,13 +159,13 @@ class Engine:
 
     # -- stage 2a ----------------------------------------------------------------------------------------
     def encode(self, feats_tm: torch.Tensor, want_enc_out: bool = False):
-        """feats_tm bf16 [B, 3002, 128] -> xkv bf16 [L_dec, B, 1500, 2, H, 64] (and enc_out bf16 [B,1500,d])."""
+        """feats_tm bf16 [B, 3002, 128] -> xkv bf16 [L_dec, B, H, 2, 1500, 64] (head-major; and enc_out bf16 [B,1500,d])."""
         c = self.desc
         B = feats_tm.shape[0]
         assert feats_tm.dtype == torch.bfloat16 and feats_tm.shape[1:] == (self.N_FRAMES + 2, 128)
         feats_tm = feats_tm.contiguous()
         with self._on_stream():
-            xkv = torch.empty(c["dec_layers"], B, self.F_ENC, 2, c["n_heads"], 64, dtype=torch.bfloat16, device=self.device)
+            xkv = torch.empty(c["dec_layers"], B, c["n_heads"], 2, self.F_ENC, 64, dtype=torch.bfloat16, device=self.device)
             enc = torch.empty(B, self.F_ENC, c["d_model"], dtype=torch.bfloat16, device=self.device) if want_enc_out else None
             nb = self.lib.cw_encode_workspace_bytes(self._h, B)
             ws = self._workspace("encode", nb)

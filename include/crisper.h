@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CW_ABI_VERSION 1
+#define CW_ABI_VERSION 2
 
 typedef enum cw_status {
   CW_OK = 0,
@@ -157,7 +157,8 @@ int cw_logmel(cw_ctx* ctx, const float* wave, const int32_t* n_valid, const floa
  *      encoder_attn, :326-336) --
  *  feats_tm  bf16 [B, 3002, 128]  (cw_logmel feats_tm_out)
  *  enc_out   bf16 [B, 1500, d]     last_hidden_state (may be NULL -> lives in workspace)
- *  xkv_out   bf16 [dec_layers, B, 1500, 2, n_heads, 64]   (K then V per frame)
+ *  xkv_out   bf16 [dec_layers, B, n_heads, 2, 1500, 64]   head-major: the 1500 K rows of a (layer, sample, head), then its
+ *            1500 V rows — each a contiguous 192 KB block the decode step kernel streams with bulk copies
  */
 size_t cw_encode_workspace_bytes(const cw_ctx* ctx, int B);
 int cw_encode(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xkv_out, void* ws, size_t ws_bytes,
@@ -185,10 +186,10 @@ int cw_encode(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xkv
  */
 #define CW_DEC_SUPPRESS_EOS 1     /* never pick eos (fixed-length benchmark decode) */
 #define CW_DEC_NO_TIMESTAMP_RULES 2 /* skip WhisperTimeStampLogitsProcessor (return_timestamps=False) */
-#define CW_DEC_NO_GRAPH 4         /* launch kernels directly instead of replaying a captured CUDA graph */
-#define CW_DEC_NO_MEGA 32         /* one kernel per operator instead of the persistent cooperative step kernel (B <= 8) */
-#define CW_DEC_NO_PDL 16          /* plain stream-ordered launches instead of programmatic dependent launch */
-#define CW_DEC_PROFILE 8          /* direct launches with a CUDA event after every kernel; read with cw_decode_profile */
+#define CW_DEC_NO_GRAPH 4         /* per-operator path only: launch kernels directly instead of replaying a CUDA graph */
+#define CW_DEC_NO_MEGA 32         /* one kernel per operator instead of the persistent streaming step kernel */
+#define CW_DEC_NO_PDL 16          /* per-operator path: plain stream-ordered launches instead of programmatic dependent launch */
+#define CW_DEC_PROFILE 8          /* per-operator path, direct launches with a CUDA event after every kernel; read with cw_decode_profile */
 size_t cw_decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new);
 int cw_decode_greedy(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n_prompt, int max_new,
                      int flags, const int32_t* forced, int32_t* tokens_out, int32_t* len_out, float* align_out,
@@ -240,11 +241,21 @@ long long cw_resample_out_len(long long n_in, int sr_in, int sr_out);
 size_t cw_resample_workspace_bytes(int sr_in, int sr_out);
 int cw_resample(cw_ctx* ctx, const float* x, long long n_in, int sr_in, int sr_out, float* out, long long n_out, void* ws,
                 size_t ws_bytes, void* stream);
-/* Host-only introspection of the decode step kernel's cross-attention work split (no GPU needed; used by the CPU tests):
- * `tasks` = B * n_heads (sample, head) pairs over n_frames encoder frames on n_cta persistent CTAs with 4 group slots each.
- * units_out i32 [4 * n_cta][4] = {task, range index, first frame, frame count}, task < 0 = empty slot;
- * splits_out i32 [tasks] = number of equal frame ranges of the task (3 or 4). CW_ERR_UNSUPPORTED if it does not fit. */
-int cw_decode_cross_plan(int tasks, int n_frames, int n_cta, int32_t* units_out, int32_t* splits_out);
+/* Fragment-major copies of the decoder matrices for the streaming step kernel (call once after cw_load_weights).
+ * The step kernel (default path of cw_decode_greedy) streams every weight block with one bulk copy into shared memory
+ * and reads MMA fragments from it with conflict-free 8-byte loads; for that each [N, K] matrix (self/cross attention
+ * projections, fc1/fc2, tied embedding) is re-laid out as [N/8][K/16][8][16]. The caller owns `buf`
+ * (>= cw_decode_pack_bytes(ctx) bytes, 128-byte aligned, device memory) and keeps it alive for the lifetime of the weights. */
+size_t cw_decode_pack_bytes(const cw_ctx* ctx);
+int cw_decode_pack(cw_ctx* ctx, void* buf, size_t bytes, void* stream);
+/* Host-only introspection of the step kernel's cross-attention stream plan (no GPU needed; used by the CPU tests):
+ * `tasks` = B * n_heads (sample, head) pairs over n_frames encoder frames, cut into chunks of chunk_rows frames
+ * (= d_model / 16: one ring slot of K rows + V rows), dealt as contiguous ranges to the 4 consumer groups of n_cta CTAs.
+ * items_out   i32 [tasks * ceil(n_frames / chunk_rows)][6] = {task, first frame, frames, group 0..3, segment index of the
+ *             task, flags (1 = first chunk of the group's segment, 2 = last)}, in the order every CTA's producer issues them;
+ * cta_off_out i32 [n_cta + 1] item range of CTA c = [cta_off[c], cta_off[c+1]);  splits_out i32 [tasks] segments per task. */
+int cw_decode_cross_plan(int tasks, int n_frames, int chunk_rows, int n_cta, int32_t* items_out, int32_t* cta_off_out,
+                         int32_t* splits_out);
 /* Number of kernel launches issued by this ctx since creation (bench.py `gpu_launches`). */
 long long cw_launch_count(const cw_ctx* ctx);
 /* Device time of the most recent call's dominant kernel is measured by the caller with events; these let

@@ -34,13 +34,17 @@ def _heads(x, H):
     return x.view(B, T, H, D // H).transpose(1, 2)  # [B, H, T, hd]
 
 
-def _attn(sd, p, xq, xkv, H, mask=None):
-    """WhisperAttention.forward: returns (output, attn_weights[B,H,Tq,Tk])."""
+def _attn(sd, p, xq, xkv, H, mask=None, kv=None):
+    """WhisperAttention.forward: returns (output, attn_weights[B,H,Tq,Tk]).  `kv` = (k, v) already projected and split
+    into heads (the cross-attention cache of HF, modeling_whisper.py:326-336) — same arithmetic, computed once."""
     hd = xq.shape[-1] // H
     q = (F.linear(xq, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])) * (hd ** -0.5)
-    k = F.linear(xkv, sd[p + "k_proj.weight"])
-    v = F.linear(xkv, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
-    q, k, v = _heads(q, H), _heads(k, H), _heads(v, H)
+    q = _heads(q, H)
+    if kv is None:
+        k = _heads(F.linear(xkv, sd[p + "k_proj.weight"]), H)
+        v = _heads(F.linear(xkv, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"]), H)
+    else:
+        k, v = kv
     w = torch.matmul(q, k.transpose(2, 3))
     if mask is not None:
         w = w + mask
@@ -68,7 +72,21 @@ def encoder_forward(sd: Dict[str, torch.Tensor], cfg: Dict, feats: torch.Tensor)
 
 
 @torch.no_grad()
-def decoder_forward(sd, cfg, enc_out: torch.Tensor, tokens: torch.Tensor):
+def cross_kv(sd, cfg, enc_out: torch.Tensor):
+    """The cross-attention K/V of every decoder layer (HF caches them after the first step, modeling_whisper.py:326-336):
+    list over layers of (k, v), each f32 [B, H, 1500, 64]."""
+    D = _pre(sd) + "decoder."
+    H = cfg["n_heads"]
+    out = []
+    for l in range(cfg["dec_layers"]):
+        P = f"{D}layers.{l}.encoder_attn."
+        out.append((_heads(F.linear(enc_out, sd[P + "k_proj.weight"]), H),
+                    _heads(F.linear(enc_out, sd[P + "v_proj.weight"], sd[P + "v_proj.bias"]), H)))
+    return out
+
+
+@torch.no_grad()
+def decoder_forward(sd, cfg, enc_out: torch.Tensor, tokens: torch.Tensor, xkv_cache=None):
     """Full-sequence (teacher-forced) decoder pass.  tokens i64 [B, T].
     Returns logits f32 [B, T, V] and cross-attention weights: list over layers of [B, H, T, 1500]."""
     D = _pre(sd) + "decoder."
@@ -83,7 +101,7 @@ def decoder_forward(sd, cfg, enc_out: torch.Tensor, tokens: torch.Tensor):
         a, _ = _attn(sd, P + "self_attn.", h, h, H, mask)
         x = x + a
         h = _ln(x, sd, P + "encoder_attn_layer_norm")
-        a, w = _attn(sd, P + "encoder_attn.", h, enc_out, H)
+        a, w = _attn(sd, P + "encoder_attn.", h, enc_out, H, kv=None if xkv_cache is None else xkv_cache[l])
         cross.append(w)
         x = x + a
         h = _ln(x, sd, P + "final_layer_norm")
@@ -94,7 +112,7 @@ def decoder_forward(sd, cfg, enc_out: torch.Tensor, tokens: torch.Tensor):
 
 @torch.no_grad()
 def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: int, *, suppress_eos: bool = False,
-                  timestamp_rules: bool = True, forced: Optional[np.ndarray] = None):
+                  timestamp_rules: bool = True, forced: Optional[np.ndarray] = None, xkv_cache=None):
     """Greedy loop with the Whisper logits processors.  Returns dict with
        tokens  i64 [B, n_prompt + n_gen]   (finished rows padded with eos, like HF `sequences`)
        scores  f32 [B, n_gen, V]           processed scores of every step (HF `scores`)
@@ -110,7 +128,7 @@ def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: i
     finished = np.zeros(B, bool)
     scores_all, argmax_all = [], []
     for step in range(max_new):
-        logits, _ = decoder_forward(sd, cfg, enc_out, seq)
+        logits, _ = decoder_forward(sd, cfg, enc_out, seq, xkv_cache)
         last = logits[:, -1].numpy()
         proc = np.stack([
             logits_oracle.process(last[b], seq[b, n_prompt:].tolist(), begin=(seq.shape[1] == n_prompt), eos=eos,
@@ -129,7 +147,7 @@ def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: i
             break
     n_gen = seq.shape[1] - n_prompt
     # alignment rows: one teacher-forced pass over the final sequence (identical to the incremental rows)
-    _, cross = decoder_forward(sd, cfg, enc_out, seq)
+    _, cross = decoder_forward(sd, cfg, enc_out, seq, xkv_cache)
     heads = cfg["alignment_heads"]
     if heads:
         align = torch.stack([cross[l][:, h] for l, h in heads], 1)[:, :, n_prompt:, :].numpy()

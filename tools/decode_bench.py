@@ -9,7 +9,7 @@ B = int(os.environ.get("B", "8")); T = int(os.environ.get("T", "64"))
 eng = Engine(0)
 cfg = Wt.large_v3_config()
 eng.load_weights(Wt.synthetic_weights(cfg, eng.device, seed=0))
-xkv = (torch.randn(32, B, 1500, 2, 20, 64, device="cuda") * 0.5).to(torch.bfloat16)
+xkv = (torch.randn(32, B, 20, 2, 1500, 64, device="cuda") * 0.5).to(torch.bfloat16)
 prompt = torch.tensor([[50258, 50259, 50360]] * B, dtype=torch.int32, device="cuda")
 CASES = (("mega (default)", 0), ("mega eager", L.CW_DEC_NO_GRAPH), ("ops graph+pdl", L.CW_DEC_NO_MEGA),
          ("ops eager+pdl", L.CW_DEC_NO_MEGA | L.CW_DEC_NO_GRAPH))
