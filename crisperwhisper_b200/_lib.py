@@ -15,6 +15,7 @@ CW_DEC_NO_GRAPH = 4
 CW_DEC_PROFILE = 8
 CW_DEC_NO_PDL = 16
 CW_DEC_NO_MEGA = 32
+CW_DEC_NO_SUPPRESS = 64
 
 # weight slot enums (must mirror include/crisper.h)
 W_GLOBAL = ["CONV1_W", "CONV1_B", "CONV2_W", "CONV2_B", "ENC_POS", "ENC_LNF_G", "ENC_LNF_B", "XKV_W", "XKV_B",

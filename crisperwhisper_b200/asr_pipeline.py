@@ -63,9 +63,8 @@ class AutomaticSpeechRecognitionPipeline:
             else:  # HF WhisperForConditionalGeneration (any dtype; REF/transcribe.py loads fp16 on GPU)
                 pw = Wt.pack_hf_model(model, device=self.engine.device)
                 gc = getattr(model, "generation_config", None)
-                if gc is not None:
-                    pw.config["lang_id"] = _lang_id(gc)
-                    pw.config["task_id"] = _task_id(gc)
+                # language / task / forced ids travel in pw.config (weights.config_from_hf); the prompt is resolved per
+                # call by generate.init_token_template, including per-chunk language detection when none is set
             self.engine.load_weights(pw)
         if self.engine.desc is None:
             raise RuntimeError("pipeline: the engine has no weights loaded")
@@ -101,7 +100,7 @@ class AutomaticSpeechRecognitionPipeline:
         bs = self.batch_size if batch_size is None else max(1, int(batch_size))
         cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
         waves = [A.normalize_input(x, self._resample) for x in items]
-        per_input = self._run(waves, cl, bs, gk)
+        per_input = self._run(waves, cl, bs, gk, rt)
         results = [self._postprocess(mo, rt) for mo in per_input]
         return results if is_list else results[0]
 
@@ -113,7 +112,7 @@ class AutomaticSpeechRecognitionPipeline:
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------------------
-    def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict) -> List[List[Dict]]:
+    def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict, return_timestamps="word") -> List[List[Dict]]:
         eng = self.engine
         plan = []  # (input index, start, length, left, right, is_last, with_stride)
         for wi, wave in enumerate(waves):
@@ -126,7 +125,11 @@ class AutomaticSpeechRecognitionPipeline:
         opts = G.GenOptions(max_new_tokens=gk.get("max_new_tokens"), max_length=gk.get("max_length", 448),
                             hf_batch_compat=gk.get("hf_batch_compat", self.hf_batch_compat),
                             force_unique_generate_call=bool(gk.get("force_unique_generate_call", False)),
-                            suppress_eos=bool(gk.get("suppress_eos", False)), init_tokens=gk.get("init_tokens"))
+                            suppress_eos=bool(gk.get("suppress_eos", False)), init_tokens=gk.get("init_tokens"),
+                            # HF _forward (:503-508): "word" -> token timestamps + timestamp tokens; True -> timestamp tokens
+                            # only; None/False -> <|notimestamps|> prompt and no timestamp rules
+                            return_timestamps=bool(return_timestamps), return_token_timestamps=(return_timestamps == "word"),
+                            language=gk.get("language"), task=gk.get("task"))
         stats = {"chunks": len(plan), "decode_steps": 0, "generate_passes": 0, "h2d_bytes": 0, "d2h_bytes": 0}
         outputs: List[List[Dict]] = [[] for _ in waves]
         for b0 in range(0, len(plan), batch_size):
@@ -144,7 +147,9 @@ class AutomaticSpeechRecognitionPipeline:
             eng.sync()
             res = G.generate(eng, tm, frames.cpu().numpy(), opts, stats)
             for (wi, start, length, left, right, is_last, with_stride), r in zip(items, res):
-                out = {"tokens": r["tokens"][None, :], "token_timestamps": r["token_timestamps"][None, :], "is_last": is_last}
+                out = {"tokens": r["tokens"][None, :], "is_last": is_last}
+                if opts.return_token_timestamps:
+                    out["token_timestamps"] = r["token_timestamps"][None, :]
                 if with_stride:
                     out["stride"] = (length, left, right)
                 outputs[wi].append(out)
@@ -156,7 +161,7 @@ class AutomaticSpeechRecognitionPipeline:
         """postprocess (automatic_speech_recognition.py:562-656) for the seq2seq_whisper type."""
         if self.tokenizer is None:
             return {"tokens": [o["tokens"][0] for o in model_outputs],
-                    "token_timestamps": [o["token_timestamps"][0] for o in model_outputs]}
+                    "token_timestamps": [o["token_timestamps"][0] for o in model_outputs if "token_timestamps" in o]}
         time_precision = 30.0 / self.engine.desc["n_audio_ctx"]
         for o in model_outputs:
             if "stride" in o:
@@ -167,23 +172,6 @@ class AutomaticSpeechRecognitionPipeline:
         text, optional = self._words.decode_asr(model_outputs, return_timestamps=return_timestamps,
                                                 return_language=None, time_precision=time_precision)
         return {"text": text, **optional}
-
-
-def _lang_id(gc):
-    lang = getattr(gc, "language", None)
-    table = getattr(gc, "lang_to_id", None) or {}
-    if lang is None or not table:
-        return None
-    for key in (lang, f"<|{lang}|>"):
-        if key in table:
-            return int(table[key])
-    return None
-
-
-def _task_id(gc):
-    task = getattr(gc, "task", None) or "transcribe"
-    table = getattr(gc, "task_to_id", None) or {}
-    return int(table[task]) if task in table else None
 
 
 def pipeline(task: str = "automatic-speech-recognition", model=None, **kwargs) -> AutomaticSpeechRecognitionPipeline:

@@ -560,7 +560,8 @@ __device__ __forceinline__ void sample_body(const SampleParams& p, const int b, 
       if (i >= p.Vp) continue;
       float v = v8[u];
       const uint8_t m = m8[u];
-      bool kill = (m & 4) || (m & 1) || (at_begin && (m & 2));
+      const bool sup = !(p.flags & CW_DEC_NO_SUPPRESS);
+      bool kill = (m & 4) || (sup && ((m & 1) || (at_begin && (m & 2))));
       if ((p.flags & CW_DEC_SUPPRESS_EOS) && i == p.eos) kill = true;
       if (ts_rules) {
         if (i == p.no_ts) kill = true;
@@ -722,6 +723,7 @@ struct DecBuffers {
   void* xitems; int* xitem_off; int* xsplits; float* spart;
 };
 
+static constexpr int kStreamMaxRep = 32;   // replicas of the broadcast activation vectors (see decoder_stream.cuh)
 static inline int stream_chunk_rows(const ModelDesc& m) { return m.d_model / 16; }   // K|V rows per 16*d-byte ring slot
 static inline int stream_chunks_per_task(const ModelDesc& m) {
   const int cr = stream_chunk_rows(m);
@@ -735,10 +737,11 @@ static size_t dec_layout(const ModelDesc& m, int B, int n_cta, DecBuffers* o, vo
   const size_t d = m.d_model;
   const size_t tasks = (size_t)B * m.n_heads, cpt = (size_t)stream_chunks_per_task(m);
   DecBuffers t;
-  t.x = (float*)take((size_t)B * d * 4);
+  // x, attn and hbuf exist in kStreamMaxRep identical replicas for the streaming step kernel (the per-operator path uses copy 0)
+  t.x = (float*)take((size_t)kStreamMaxRep * B * d * 4);
   t.qbuf = (float*)take((size_t)B * d * 4);
-  t.attn = (bf16*)take((size_t)B * d * 2);
-  t.hbuf = (bf16*)take((size_t)B * m.ffn_dim * 2);
+  t.attn = (bf16*)take((size_t)kStreamMaxRep * B * d * 2);
+  t.hbuf = (bf16*)take((size_t)kStreamMaxRep * B * m.ffn_dim * 2);
   t.xn = (bf16*)take((size_t)B * d * 2);
   t.logits = (float*)take((size_t)B * m.vocab_padded * 4);
   t.kc = (bf16*)take((size_t)m.dec_layers * B * m.n_text_ctx * d * 2);   // [L][B][H][n_ctx][64]
@@ -754,7 +757,7 @@ static size_t dec_layout(const ModelDesc& m, int B, int n_cta, DecBuffers* o, vo
   t.xcount = (unsigned int*)take(tasks * 4);
   t.spart = (float*)take((size_t)2 * B * n_cta * 8 * 4);
   t.bar = (unsigned int*)take(256);
-  t.dbg = (unsigned long long*)take(32 * 8);
+  t.dbg = (unsigned long long*)take(128 * 8);
   t.prog = take((size_t)(8 * m.dec_layers + 4) * 128);
   if (o) *o = t;
   return a.off + 256;
@@ -916,7 +919,7 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
 // the producer issues them: round-robin over its 4 groups.
 static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XItem>* items, std::vector<int>* cta_off,
                             std::vector<int>* splits) {
-  if (tasks < 1 || F < 1 || cr < 1 || n_cta < 1) return -1;
+  if (tasks < 1 || F < 1 || F > 32767 || cr < 1 || n_cta < 1) return -1;
   const int cpt = (F + cr - 1) / cr;
   const long long U = (long long)tasks * cpt, NG = 4LL * n_cta;
   splits->assign(tasks, 0);
@@ -931,11 +934,12 @@ static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XIt
       for (long long u = u0; u < u1; ++u) {
         const int task = (int)(u / cpt), ch = (int)(u % cpt);
         XItem it;
-        it.task = task; it.f0 = ch * cr; it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr); it.group = (short)gi;
+        memset(&it, 0, sizeof(it));
+        it.task = task; it.f0 = (short)(ch * cr); it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr); it.group = (signed char)gi;
         const bool first = (u == u0) || ch == 0, last = (u == u1 - 1) || ch == cpt - 1;
         if (first) (*splits)[task] += 1;
         it.seg = (short)((*splits)[task] - 1);
-        it.flags = (short)((first ? 1 : 0) | (last ? 2 : 0));
+        it.flags = (signed char)((first ? 1 : 0) | (last ? 2 : 0));
         grp[gi].push_back(it);
       }
     }
@@ -946,6 +950,7 @@ static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XIt
         if (ci < grp[gi].size()) items->push_back(grp[gi][ci]);
     (*cta_off)[(size_t)c + 1] = (int)items->size();
   }
+  for (XItem& it : *items) it.ns = (short)(*splits)[it.task];
   return 0;
 }
 
@@ -1034,10 +1039,11 @@ struct StreamCfg { int NS, ns_log, SB, CR, TB, XR, xs_off, red_off; size_t smem;
 
 static bool stream_config(const ModelDesc& m, int B, StreamCfg* c) {
   const int d = m.d_model;
-  if (d % 128 != 0 || d > 16 * 16 * kSKsMax || m.ffn_dim % d != 0 || B > 16 || m.n_text_ctx > 448) return false;
+  if (d % 128 != 0 || d > 16 * 16 * kSKsMax || m.ffn_dim % d != 0 || m.ffn_dim > 4 * d || B > 16 || m.n_text_ctx > 448) return false;
+  if (m.dec_layers * m.n_heads > kSMaxAmap) return false;
   c->SB = 16 * d; c->CR = d / 16; c->XR = (B > 8) ? 16 : 8;
   const size_t xs_bytes = align_up((size_t)c->XR * (d + 16) * 2, 128);
-  const size_t limit = 227 * 1024 - 1024;   // static smem (barriers, flags) + slack
+  const size_t limit = 227 * 1024 - 8192;   // static smem: barriers, flags, stream items, head map, phase descriptors
   for (int ns = kSMaxSlots; ns >= 2; ns >>= 1)
     for (int tb = 4; tb >= 2; tb >>= 1) {
       const size_t red_bytes = (size_t)16 * tb * 128 * 4;
@@ -1064,6 +1070,8 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
   p.V = m.vocab; p.dec_layers = m.dec_layers;
   p.G = G; p.NS = sc.NS; p.ns_log = sc.ns_log; p.SB = sc.SB; p.CR = sc.CR; p.TB = sc.TB; p.XR = sc.XR;
   p.xs_off = sc.xs_off; p.red_off = sc.red_off;
+  p.R = 1;
+  if (const char* e = getenv("CW_STREAM_REP")) { p.R = atoi(e); if (p.R < 1) p.R = 1; if (p.R > kStreamMaxRep) p.R = kStreamMaxRep; }
   p.x = bf.x; p.qbuf = bf.qbuf; p.attn = bf.attn; p.hbuf = bf.hbuf; p.kc = bf.kc; p.vc = bf.vc;
   p.st = bf.st; p.seq = bf.seq; p.finished = bf.finished; p.xkv = xkv;
   p.tok_emb = (const bf16*)ctx->w[CW_W_TOK_EMB]; p.dec_pos = (const float*)ctx->w[CW_W_DEC_POS];
@@ -1080,6 +1088,9 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
     std::vector<int> off, splits;
     CW_REQUIRE(plan_cross_items(B * m.n_heads, m.n_audio_ctx, sc.CR, G, &items, &off, &splits) == 0, CW_ERR_UNSUPPORTED,
                "decode step kernel: cannot lay out %d cross-attention tasks on %d CTAs", B * m.n_heads, G);
+    for (int c = 0; c < G; ++c)
+      CW_REQUIRE(off[(size_t)c + 1] - off[c] <= kSMaxItems, CW_ERR_UNSUPPORTED,
+                 "decode step kernel: %d cross-attention items on one CTA (max %d)", off[(size_t)c + 1] - off[c], kSMaxItems);
     CW_CUDA(cudaMemcpyAsync(bf.xitems, items.data(), items.size() * sizeof(XItem), cudaMemcpyHostToDevice, st));
     CW_CUDA(cudaMemcpyAsync(bf.xitem_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     CW_CUDA(cudaMemcpyAsync(bf.xsplits, splits.data(), splits.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1127,7 +1138,7 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
   }
   gemv_ph(9, EPI_LOGITS, m.vocab_padded, d_, pk + pt.off.back(), nullptr, ctx->w[CW_W_DEC_LNF_G], ctx->w[CW_W_DEC_LNF_B], bf.x, nullptr,
           nullptr, nullptr, nullptr, nullptr);
-  CW_REQUIRE(prog.size() <= (size_t)(8 * m.dec_layers + 4), CW_ERR_INVALID, "decode program too long");
+  CW_REQUIRE(prog.size() <= (size_t)(8 * m.dec_layers + 4) && prog.size() % 2 == 0, CW_ERR_INVALID, "decode program length");
   CW_CUDA(cudaMemcpyAsync(bf.prog, prog.data(), prog.size() * sizeof(SPhase), cudaMemcpyHostToDevice, st));
   p.prog = (const SPhase*)bf.prog;
   p.n_phases = (int)prog.size();
@@ -1155,7 +1166,7 @@ __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_l
                                 int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) { st->pos = 0; st->n_finished = 0; st->bar_epoch = 0u; *bar = 0u; }
-  if (i < 32) dbg[i] = 0ull;
+  if (i < 128) dbg[i] = 0ull;
   if (i < n_xcount) xcount[i] = 0u;
   if (i < B) finished[i] = 0;
   if (i < B * seq_ld) {
@@ -1235,13 +1246,22 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
     // tokens exist for positions < s (the token of position s is sampled by the next launch / the tail)
     steps_done = stopped ? std::max(0, s - n_prompt) : max_new;
     if (getenv("CW_MEGA_DEBUG")) {
-      unsigned long long h[32];
+      unsigned long long h[128];
       CW_CUDA(cudaStreamSynchronize(st));
       CW_CUDA(cudaMemcpy(h, bf.dbg, sizeof(h), cudaMemcpyDeviceToHost));
       static const char* nm[] = {"sample+emb", "qkv", "self_attn", "o_proj", "q_cross", "cross_attn", "oc_proj", "fc1", "fc2", "logits"};
-      fprintf(stderr, "[CW_MEGA_DEBUG] CTA1 ns per step (compute / barrier wait), %d steps\n", s);
+      fprintf(stderr, "[CW_MEGA_DEBUG] CTA1 ns per step (phase body / grid-barrier wait / of the body: waiting for the stream), %d steps\n", s);
       for (int i = 0; i < 10; ++i)
-        fprintf(stderr, "  %-10s %9.0f / %9.0f\n", nm[i], (double)h[2 * i] / s, (double)h[2 * i + 1] / s);
+        fprintf(stderr, "  %-10s %9.0f / %9.0f / %9.0f\n", nm[i], (double)h[2 * i] / s, (double)h[2 * i + 1] / s, (double)h[20 + i] / s);
+#ifdef CW_STREAM_PROF
+      fprintf(stderr, "[CW_STREAM_PROF] sub-phase ns per step: gemv {1 LN staged, 2 fragments requested, 3 MMA+partials, 4 CTA barrier, 5 epilogue} "
+                      "self {1 chunks, 2 new row+merge} cross {1 chunks, 2 publish, 3 merge/tail} barrier {6 CTA arrive, 7 grid poll}\n");
+      for (int i = 0; i < 10; ++i) {
+        fprintf(stderr, "  %-10s", nm[i]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %8.0f", (double)h[32 + 8 * i + k] / s);
+        fprintf(stderr, "\n");
+      }
+#endif
     }
   } else {
     // ---- one kernel per operator (cross-check of the step kernel, CW_DEC_PROFILE) ----

@@ -41,7 +41,10 @@ class GenOptions:
     force_unique_generate_call: bool = False
     suppress_eos: bool = False             # benchmark mode (fixed decode length)
     init_tokens: Optional[List[int]] = None
-    return_timestamps: bool = True
+    return_timestamps: bool = True         # timestamp tokens + WhisperTimeStampLogitsProcessor (pipeline: True or "word")
+    return_token_timestamps: bool = True   # alignment-head DTW word timing (pipeline: "word")
+    language: Optional[object] = None      # generate_kwargs["language"]: str or per-row list (HF :1530-1552)
+    task: Optional[str] = None             # generate_kwargs["task"]
 
 
 def _max_new(cfg: Dict, opts: GenOptions, n_prompt: int) -> int:
@@ -127,8 +130,8 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
     of all seek passes concatenated (no prompt), as HF's `sequences` / `segments` before batch padding."""
     cfg = engine.desc
     B = feats_tm.shape[0]
-    init = list(opts.init_tokens) if opts.init_tokens is not None else default_init_tokens(cfg)
-    n_prompt = len(init)
+    init_rows, need_detect = init_token_template(cfg, opts, B)   # per-row prompts; language slot filled on the first pass
+    n_prompt = len(init_rows[0])
     ts_begin = cfg["no_timestamps_id"] + 1
     eos = cfg["eos_id"]
     max_new = _max_new(cfg, opts, n_prompt)
@@ -160,8 +163,14 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
             sl = slice(g0, min(g0 + MAX_DECODE_BATCH, len(active)))
             nb = sl.stop - sl.start
             xkv, _ = engine.encode(seg_in[sl])
-            prompt = torch.tensor([init] * nb, dtype=torch.int32, device=engine.device)
-            out = engine.decode(xkv, prompt, max_new, flags=flags)
+            rows_g = active[sl]
+            if need_detect and n_pass == 0:   # HF detects once per generate call, on the first window of every row
+                for i, lid in zip(rows_g, detect_language(engine, xkv, cfg, nb)):
+                    init_rows[i][1] = lid
+                if stats is not None:
+                    stats["language_detect_calls"] = stats.get("language_detect_calls", 0) + 1
+            prompt = torch.tensor([init_rows[i] for i in rows_g], dtype=torch.int32, device=engine.device)
+            out = engine.decode(xkv, prompt, max_new, flags=flags, want_align=opts.return_token_timestamps)
             engine.sync()
             if stats is not None:
                 stats["decode_steps"] = stats.get("decode_steps", 0) + out["steps"]
@@ -182,7 +191,7 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
             F_len = crop(np.full(nb, F_full), k)
             if len(np.unique(k)) == 1:
                 F_len = crop(F_len, k)
-            if out["align"] is not None and T_rows.max() > 0:
+            if opts.return_token_timestamps and out["align"] is not None and T_rows.max() > 0:
                 j = engine.align(out["align"], torch.from_numpy(T_rows.astype(np.int32)),
                                  torch.from_numpy(np.maximum(F_len, 1).astype(np.int32)), cfg["median_filter_width"])
                 engine.sync()
@@ -228,19 +237,127 @@ def generate(engine, feats_tm: torch.Tensor, num_frames: np.ndarray, opts: GenOp
             tts = np.concatenate([s["token_timestamps"] for s in segs])
         else:
             tokens, tts = np.zeros(0, np.int64), np.zeros(0, np.float32)
-        results.append({"tokens": tokens, "token_timestamps": tts, "segments": segs})
+        results.append({"tokens": tokens, "token_timestamps": tts, "segments": segs, "init_tokens": list(init_rows[i])})
     return results
 
 
-def default_init_tokens(cfg: Dict) -> List[int]:
-    """[<|startoftranscript|>, language, task] (_retrieve_init_tokens, generation_whisper.py:1455-1608); no
-    <|notimestamps|> because timestamps are returned."""
+def language_to_id(cfg: Dict, language: str) -> int:
+    """language_to_id of HF's _retrieve_init_tokens (generation_whisper.py:1465-1487): accepts "<|en|>", "en" or "english"."""
+    table = cfg.get("lang_to_id") or {}
+    lang = str(language).lower()
+    if lang in table:
+        token = lang
+    else:
+        try:
+            from transformers.models.whisper.tokenization_whisper import TO_LANGUAGE_CODE
+        except Exception:  # transformers is the caller's dependency (tokenizer); without it only codes are understood
+            TO_LANGUAGE_CODE = {}
+        if lang in TO_LANGUAGE_CODE:
+            token = f"<|{TO_LANGUAGE_CODE[lang]}|>"
+        elif lang in TO_LANGUAGE_CODE.values() or (not TO_LANGUAGE_CODE and f"<|{lang}|>" in table):
+            token = f"<|{lang}|>"
+        else:
+            raise ValueError(f"Unsupported language: {language}.")
+    if token not in table:
+        raise ValueError(f"{token} is not supported by this specific model as it is not in the `generation_config.lang_to_id`.")
+    return int(table[token])
+
+
+def init_token_template(cfg: Dict, opts: GenOptions, batch_size: int):
+    """Decoder prompt per row, following HF's _retrieve_init_tokens (generation_whisper.py:1455-1608):
+    [<|startoftranscript|>, language, task, (<|notimestamps|>)].  Returns (rows, detect): `rows` is a list of
+    `batch_size` id lists; when `detect` is True the language slot (index 1) holds None and must be filled with the
+    ids cw_decode_greedy's language-detection step returns (HF detect_language :1612-1672).
+    Synthetic configs without the generation_config tables may pin `lang_id` / `task_id` directly."""
+    if opts.init_tokens is not None:
+        return [list(opts.init_tokens) for _ in range(batch_size)], False
     sot = cfg.get("decoder_start_token_id")
     if sot is None:
         raise ValueError("config lacks decoder_start_token_id")
-    out = [int(sot)]
-    if cfg.get("lang_id") is not None:
-        out.append(int(cfg["lang_id"]))
-    if cfg.get("task_id") is not None:
-        out.append(int(cfg["task_id"]))
-    return out
+    lang_to_id, task_to_id = cfg.get("lang_to_id") or {}, cfg.get("task_to_id") or {}
+    language = opts.language if opts.language is not None else cfg.get("language")
+    task = opts.task if opts.task is not None else cfg.get("task")
+    init: List[Optional[int]] = [int(sot)]
+    if task is None and language is None and cfg.get("lang_id") is None:
+        fdi = cfg.get("forced_decoder_ids")   # deprecated HF flag, kept for old checkpoints (:1494-1527)
+        if fdi and fdi[0][0] == 1:
+            fdi = [list(x) for x in fdi]
+            i = 1
+            while fdi and fdi[0][0] == i:
+                init.append(fdi[0][1])
+                fdi = fdi[1:]
+                i += 1
+            if fdi:
+                raise ValueError("forced_decoder_ids do not follow the prompt pattern of Whisper")
+    undefined = len(init) <= 1 or init[1] is None
+    if isinstance(language, (list, tuple)):
+        if any(l is None for l in language) or len(language) != batch_size:
+            raise ValueError("a list of languages must hold one language per batch row")
+        languages = list(language)
+    elif language is None:
+        languages = [None] * batch_size
+    else:
+        languages = [language] * batch_size
+    rows = [list(init) for _ in range(batch_size)]
+    detect = False
+    lang_ids = None
+    if language is not None:
+        lang_ids = [language_to_id(cfg, l) for l in languages]
+    elif cfg.get("lang_id") is not None and undefined:
+        lang_ids = [int(cfg["lang_id"])] * batch_size
+    elif lang_to_id and undefined:
+        lang_ids, detect = [None] * batch_size, True
+    elif cfg.get("is_multilingual") and undefined:
+        raise ValueError("multilingual model without a language: set generation_config.language / lang_to_id "
+                         "(or pass generate_kwargs={'language': ...}); no language token can be resolved")
+    if lang_ids is not None:
+        for r, lid in zip(rows, lang_ids):
+            if len(r) > 1:
+                r[1] = lid
+            else:
+                r.append(lid)
+    for r in rows:
+        if task is not None:
+            if task in task_to_id:
+                tid = int(task_to_id[task])
+            elif cfg.get("task_id") is not None:
+                tid = int(cfg["task_id"])
+            else:
+                raise ValueError(f"The `{task}` task is not supported.")
+            if any(t in task_to_id.values() for t in r if t is not None):
+                r[:] = [tid if (t is not None and t in task_to_id.values()) else t for t in r]
+            else:
+                r.append(tid)
+        elif language is not None and task_to_id:
+            if not any(t in task_to_id.values() for t in r if t is not None):
+                r.append(int(task_to_id["transcribe"]))
+        elif cfg.get("task_id") is not None and not task_to_id:
+            r.append(int(cfg["task_id"]))
+        no_ts = cfg["no_timestamps_id"]
+        if not opts.return_timestamps and r[-1] != no_ts:
+            r.append(int(no_ts))
+        elif opts.return_timestamps and r[-1] == no_ts:
+            r.pop()
+    keep = [[k for k, t in enumerate(r) if t is not None or (detect and k == 1)] for r in rows]
+    rows = [[r[k] for k in ks] for r, ks in zip(rows, keep)]
+    return rows, detect
+
+
+def detect_language(engine, xkv, cfg: Dict, n_rows: int) -> List[int]:
+    """HF detect_language (generation_whisper.py:1612-1672): one decoder step on [<|startoftranscript|>], logits restricted
+    to the language ids, argmax — per row.  Runs on the step kernel with the raw (unsuppressed, rule-free) logits."""
+    sot = int(cfg["decoder_start_token_id"])
+    prompt = torch.tensor([[sot]] * n_rows, dtype=torch.int32, device=engine.device)
+    out = engine.decode(xkv, prompt, 1, flags=L.CW_DEC_NO_TIMESTAMP_RULES | L.CW_DEC_NO_SUPPRESS | L.CW_DEC_SUPPRESS_EOS * 0,
+                        want_logits=True, want_align=False)
+    engine.sync()
+    ids = sorted(int(v) for v in (cfg.get("lang_to_id") or {}).values())
+    logits = out["logits"][:, 0, :].float().cpu().numpy()
+    sel = logits[:, ids]
+    return [ids[int(k)] for k in sel.argmax(-1)]
+
+
+def default_init_tokens(cfg: Dict) -> List[int]:
+    """Prompt of a batch-size-1 call with default options (kept for callers that only need the prompt length)."""
+    rows, detect = init_token_template(cfg, GenOptions(), 1)
+    return [t if t is not None else -1 for t in rows[0]]

@@ -129,7 +129,14 @@ def config_from_hf(model, generation_config=None) -> Dict:
     eos = gc.eos_token_id if gc.eos_token_id is not None else hc.eos_token_id
     if isinstance(eos, (list, tuple)):
         eos = eos[0]
+    # prompt-token resolution fields (language / task / forced ids; generate.init_token_template follows HF's
+    # _retrieve_init_tokens, generation_whisper.py:1455-1608)
+    extra = dict(lang_to_id=dict(getattr(gc, "lang_to_id", None) or {}), task_to_id=dict(getattr(gc, "task_to_id", None) or {}),
+                 language=getattr(gc, "language", None), task=getattr(gc, "task", None),
+                 is_multilingual=bool(getattr(gc, "is_multilingual", False)),
+                 forced_decoder_ids=getattr(gc, "forced_decoder_ids", None) or getattr(hc, "forced_decoder_ids", None))
     return make_config(
+        **extra,
         d_model=hc.d_model, n_heads=hc.encoder_attention_heads, enc_layers=hc.encoder_layers,
         dec_layers=hc.decoder_layers, ffn_dim=hc.encoder_ffn_dim, vocab=hc.vocab_size, n_mels=hc.num_mel_bins,
         eos_id=int(eos), no_timestamps_id=int(gc.no_timestamps_token_id), alignment_heads=heads,

@@ -189,6 +189,8 @@ int cw_encode(cw_ctx* ctx, const void* feats_tm, int B, void* enc_out, void* xkv
 #define CW_DEC_NO_GRAPH 4         /* per-operator path only: launch kernels directly instead of replaying a CUDA graph */
 #define CW_DEC_NO_MEGA 32         /* one kernel per operator instead of the persistent streaming step kernel */
 #define CW_DEC_NO_PDL 16          /* per-operator path: plain stream-ordered launches instead of programmatic dependent launch */
+#define CW_DEC_NO_SUPPRESS 64      /* skip the SuppressTokens / SuppressTokensAtBegin lists (raw logits for language detection,
+                                     HF/models/whisper/generation_whisper.py:1660-1672); padding rows stay masked */
 #define CW_DEC_PROFILE 8          /* per-operator path, direct launches with a CUDA event after every kernel; read with cw_decode_profile */
 size_t cw_decode_workspace_bytes(const cw_ctx* ctx, int B, int max_new);
 int cw_decode_greedy(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n_prompt, int max_new,

@@ -112,7 +112,7 @@ def decoder_forward(sd, cfg, enc_out: torch.Tensor, tokens: torch.Tensor, xkv_ca
 
 @torch.no_grad()
 def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: int, *, suppress_eos: bool = False,
-                  timestamp_rules: bool = True, forced: Optional[np.ndarray] = None, xkv_cache=None):
+                  timestamp_rules: bool = True, forced: Optional[np.ndarray] = None, xkv_cache=None, no_suppress: bool = False):
     """Greedy loop with the Whisper logits processors.  Returns dict with
        tokens  i64 [B, n_prompt + n_gen]   (finished rows padded with eos, like HF `sequences`)
        scores  f32 [B, n_gen, V]           processed scores of every step (HF `scores`)
@@ -123,7 +123,7 @@ def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: i
     Every step recomputes the full prefix (O(T^2)) — fine for the small oracle configurations."""
     B, n_prompt = prompt.shape
     eos, no_ts = cfg["eos_id"], cfg["no_timestamps_id"]
-    suppress = list(cfg.get("suppress_tokens") or []) + ([eos] if suppress_eos else [])
+    suppress = ([] if no_suppress else list(cfg.get("suppress_tokens") or [])) + ([eos] if suppress_eos else [])
     seq = torch.from_numpy(prompt.astype(np.int64))
     finished = np.zeros(B, bool)
     scores_all, argmax_all = [], []
@@ -132,7 +132,7 @@ def greedy_decode(sd, cfg, enc_out: torch.Tensor, prompt: np.ndarray, max_new: i
         last = logits[:, -1].numpy()
         proc = np.stack([
             logits_oracle.process(last[b], seq[b, n_prompt:].tolist(), begin=(seq.shape[1] == n_prompt), eos=eos,
-                                  no_ts=no_ts, suppress=suppress, begin_suppress=cfg.get("begin_suppress_tokens") or [],
+                                  no_ts=no_ts, suppress=suppress, begin_suppress=[] if no_suppress else (cfg.get("begin_suppress_tokens") or []),
                                   max_initial_timestamp_index=cfg.get("max_initial_timestamp_index"),
                                   timestamp_rules=timestamp_rules)
             for b in range(B)])

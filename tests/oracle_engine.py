@@ -44,7 +44,7 @@ class OracleEngine:
 
     def decode(self, xkv, prompt, max_new, flags=0, forced=None, want_logits=False, want_align=True):
         out = R.greedy_decode(self.sd, self.desc, xkv, prompt.numpy().astype(np.int64), max_new,
-                              suppress_eos=bool(flags & 1), timestamp_rules=not (flags & 2))
+                              suppress_eos=bool(flags & 1), timestamp_rules=not (flags & 2), no_suppress=bool(flags & 64))
         B, n_prompt = prompt.shape
         toks = out["tokens"]
         n_gen = toks.shape[1] - n_prompt
@@ -65,8 +65,13 @@ class OracleEngine:
         H_a = len(self.desc["alignment_heads"])
         align = torch.zeros(B, H_a, max_new, 1500)
         align[:, :, :n_gen] = torch.from_numpy(out["align"])
-        return dict(tokens=torch.from_numpy(full.astype(np.int32)), lengths=torch.from_numpy(lens), align=align, logits=None,
-                    argmax=None, steps=n_gen)
+        logits = None
+        if want_logits:
+            lg = np.full((B, max_new, out["scores"].shape[-1]), -np.inf, np.float32)
+            lg[:, :n_gen] = out["scores"]
+            logits = torch.from_numpy(lg)
+        return dict(tokens=torch.from_numpy(full.astype(np.int32)), lengths=torch.from_numpy(lens),
+                    align=align if want_align else None, logits=logits, argmax=None, steps=n_gen)
 
     def align(self, align, T_len, F_len, median_width=7):
         a = align.numpy()
