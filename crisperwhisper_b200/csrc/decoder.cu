@@ -720,7 +720,7 @@ struct DecBuffers {
   float* x; float* qbuf; bf16* attn; bf16* hbuf; bf16* xn; float* logits;
   bf16* kc; bf16* vc; DecState* st; int* finished; int* seq;
   float* xpart; float* xscore; unsigned int* xcount; unsigned int* bar; unsigned long long* dbg; void* prog;
-  void* xitems; int* xitem_off; int* xsplits; float* spart;
+  void* xitems; int* xitem_off; int* xsplits; float* spart; float* kpart; unsigned int* kflag;
 };
 
 static constexpr int kStreamMaxRep = 32;   // replicas of the broadcast activation vectors (see decoder_stream.cuh)
@@ -756,8 +756,10 @@ static size_t dec_layout(const ModelDesc& m, int B, int n_cta, DecBuffers* o, vo
   t.xscore = (float*)take(tasks * m.n_audio_ctx * 4);
   t.xcount = (unsigned int*)take(tasks * 4);
   t.spart = (float*)take((size_t)2 * B * n_cta * 8 * 4);
+  t.kpart = (float*)take((size_t)(n_cta / 4 + 1) * 3 * 8 * 128 * 4);
+  t.kflag = (unsigned int*)take((size_t)(n_cta / 4 + 1) * 4);
   t.bar = (unsigned int*)take(256);
-  t.dbg = (unsigned long long*)take(128 * 8);
+  t.dbg = (unsigned long long*)take((128 + 2048) * 8);
   t.prog = take((size_t)(8 * m.dec_layers + 4) * 128);
   if (o) *o = t;
   return a.off + 256;
@@ -912,36 +914,64 @@ static int enqueue_step(cw_ctx* ctx, const DecBuffers& bf, const bf16* xkv, int 
 // ---------------------------------------------------------------------------------------------------------
 // Streaming step kernel: host side (plan, packing, launch)
 // ---------------------------------------------------------------------------------------------------------
-// Cross-attention plan: every (sample, head) task is cut into chunks of `cr` frames (one ring slot each); the tasks x
-// chunks units are dealt as contiguous ranges to the 4 x n_cta consumer groups, so that every group streams the same
-// number of chunks (+-1) and a CTA walks a contiguous region of the head-major K/V tensor. The part of a task that lands
-// in one group is a segment (its partial softmax is merged by the last arriver). Items of a CTA are emitted in the order
-// the producer issues them: round-robin over its 4 groups.
+// Cross-attention plan: every (sample, head) task is cut into chunks of `cr` frames (one ring slot each) and the chunks of a
+// task into ns contiguous segments of (nearly) equal length, ns = floor or ceil of (4 x n_cta) / tasks, so that every one of
+// the 4 consumer groups of every CTA owns exactly ONE segment (one online-softmax state, one finalisation at the very end of
+// the phase: a group that had to finish one task and start another in mid-phase cost ~5 us per layer). Segments are dealt
+// to the CTAs longest-first (each to the least-loaded CTA with a free group), which balances the chunks per CTA to +-1.
+// Items of a CTA are emitted in the order its producer issues them: round-robin over its groups.
+// More tasks than groups (B > 18 at 148 SMs): a group takes several whole tasks, one after the other.
 static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XItem>* items, std::vector<int>* cta_off,
                             std::vector<int>* splits) {
   if (tasks < 1 || F < 1 || F > 32767 || cr < 1 || n_cta < 1) return -1;
   const int cpt = (F + cr - 1) / cr;
-  const long long U = (long long)tasks * cpt, NG = 4LL * n_cta;
-  splits->assign(tasks, 0);
+  const int NG = 4 * n_cta;
+  struct Seg { int task, seg, c0, nc; };
+  std::vector<Seg> segs;
+  splits->assign(tasks, 1);
+  const int base = std::max(1, std::min(cpt, NG / tasks));
+  int extra = (NG / tasks >= 1 && base < cpt) ? NG - base * tasks : 0;   // tasks that get one more segment
+  for (int t = 0; t < tasks; ++t) {
+    int ns = base;
+    if (extra > 0 && ns < cpt) { ns += 1; extra -= 1; }
+    (*splits)[t] = ns;
+    int c0 = 0;
+    for (int i = 0; i < ns; ++i) {
+      const int nc = cpt / ns + (i < cpt % ns ? 1 : 0);
+      segs.push_back({t, i, c0, nc});
+      c0 += nc;
+    }
+  }
+  std::stable_sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.nc > b.nc; });
+  // group slot g of CTA c holds a list of segments (exactly one while tasks <= NG)
+  std::vector<std::vector<Seg>> slot((size_t)NG);
+  std::vector<int> load(n_cta, 0), used(n_cta, 0);
+  const int per_slot = (int)((segs.size() + NG - 1) / NG);   // segments a group may hold
+  for (const Seg& sg : segs) {
+    int best = -1;
+    for (int c = 0; c < n_cta; ++c)
+      if (used[c] < 4 * per_slot && (best < 0 || load[c] < load[best])) best = c;
+    if (best < 0) return -1;
+    slot[(size_t)best * 4 + used[best] % 4].push_back(sg);
+    used[best] += 1;
+    load[best] += sg.nc;
+  }
   items->clear();
   cta_off->assign((size_t)n_cta + 1, 0);
   std::vector<XItem> grp[4];
   for (int c = 0; c < n_cta; ++c) {
     for (int gi = 0; gi < 4; ++gi) {
       grp[gi].clear();
-      const long long gg = 4LL * c + gi;
-      const long long u0 = gg * U / NG, u1 = (gg + 1) * U / NG;
-      for (long long u = u0; u < u1; ++u) {
-        const int task = (int)(u / cpt), ch = (int)(u % cpt);
-        XItem it;
-        memset(&it, 0, sizeof(it));
-        it.task = task; it.f0 = (short)(ch * cr); it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr); it.group = (signed char)gi;
-        const bool first = (u == u0) || ch == 0, last = (u == u1 - 1) || ch == cpt - 1;
-        if (first) (*splits)[task] += 1;
-        it.seg = (short)((*splits)[task] - 1);
-        it.flags = (signed char)((first ? 1 : 0) | (last ? 2 : 0));
-        grp[gi].push_back(it);
-      }
+      for (const Seg& sg : slot[(size_t)c * 4 + gi])
+        for (int k = 0; k < sg.nc; ++k) {
+          const int ch = sg.c0 + k;
+          XItem it;
+          memset(&it, 0, sizeof(it));
+          it.task = sg.task; it.f0 = (short)(ch * cr); it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr);
+          it.group = (signed char)gi; it.seg = (short)sg.seg; it.ns = (short)(*splits)[sg.task];
+          it.flags = (signed char)((k == 0 ? 1 : 0) | (k == sg.nc - 1 ? 2 : 0));
+          grp[gi].push_back(it);
+        }
     }
     size_t mx = 0;
     for (int gi = 0; gi < 4; ++gi) mx = std::max(mx, grp[gi].size());
@@ -950,7 +980,6 @@ static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XIt
         if (ci < grp[gi].size()) items->push_back(grp[gi][ci]);
     (*cta_off)[(size_t)c + 1] = (int)items->size();
   }
-  for (XItem& it : *items) it.ns = (short)(*splits)[it.task];
   return 0;
 }
 
@@ -1078,7 +1107,7 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
   p.align_map = ctx->d_align_map; p.align_out = align_out; p.H_a = m.n_align_heads; p.T_cap = max_new; p.n_prompt = n_prompt;
   p.xpart = bf.xpart; p.xscore = bf.xscore; p.xcount = bf.xcount; p.xsplits = bf.xsplits;
   p.part_stride = stream_chunks_per_task(m);
-  p.bar = bf.bar; p.spart = bf.spart;
+  p.bar = bf.bar; p.spart = bf.spart; p.kpart = bf.kpart; p.kflag = bf.kflag;
   p.dbg = getenv("CW_MEGA_DEBUG") ? bf.dbg : nullptr;
   p.suppress = ctx->d_suppress; p.max_new = max_new; p.eos = m.eos_id; p.no_ts = m.no_timestamps_id;
   p.max_initial_ts = m.max_initial_timestamp_index; p.flags = flags;
@@ -1104,6 +1133,8 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
   const bf16* pk = (const bf16*)ctx->pack_buf;
   std::vector<SPhase> prog;
   int rot = 0;
+  // fc2 as K-split groups: needs 4 | #CTAs, K = 4 d and at most 8 tiles per group
+  const bool fc2_groups = (G % 4 == 0) && (m.ffn_dim == 4 * m.d_model) && ((m.d_model / 8 + G / 4 - 1) / (G / 4) <= 8) && !getenv("CW_STREAM_NO_FC2G");
   auto gemv_ph = [&](int slot, int epi, int N, int K, const bf16* Wp, const void* bias, const void* g, const void* bt,
                      const float* src_f32, const bf16* src_bf16, float* out_f32, bf16* out_bf16, bf16* kcp, bf16* vcp) {
     SPhase ph;
@@ -1113,6 +1144,7 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
     ph.src_f32 = src_f32; ph.src_bf16 = src_bf16; ph.out_f32 = out_f32; ph.out_bf16 = out_bf16; ph.kcache = kcp; ph.vcache = vcp;
     prog.push_back(ph);
     rot = (rot + G - (N / 8) % G) % G;   // the CTAs that got the remainder tiles of this phase are not the next phase's
+    if (slot == 8) rot = 0;               // every layer repeats the same split (the kernel caches it per phase kind)
   };
   auto simple_ph = [&](int type, int slot, int l) {
     SPhase ph;
@@ -1135,6 +1167,7 @@ static int stream_upload_params(cw_ctx* ctx, const DecBuffers& bf, const StreamC
     gemv_ph(6, EPI_RESID, d_, d_, pk + po[3], Lw[CW_DL_BOC], nullptr, nullptr, nullptr, bf.attn, bf.x, nullptr, nullptr, nullptr);
     gemv_ph(7, EPI_GELU_BF16, m.ffn_dim, d_, pk + po[4], Lw[CW_DL_B1], Lw[CW_DL_LN3_G], Lw[CW_DL_LN3_B], bf.x, nullptr, nullptr, bf.hbuf, nullptr, nullptr);
     gemv_ph(8, EPI_RESID, d_, m.ffn_dim, pk + po[5], Lw[CW_DL_B2], nullptr, nullptr, nullptr, bf.hbuf, bf.x, nullptr, nullptr, nullptr);
+    if (fc2_groups) { prog.back().rot = -1; prog.back().l = l; }   // K-split groups of 4 CTAs (decoder_stream.cuh, s_ph_fc2g)
   }
   gemv_ph(9, EPI_LOGITS, m.vocab_padded, d_, pk + pt.off.back(), nullptr, ctx->w[CW_W_DEC_LNF_G], ctx->w[CW_W_DEC_LNF_B], bf.x, nullptr,
           nullptr, nullptr, nullptr, nullptr);
@@ -1163,11 +1196,13 @@ static int launch_stream(cw_ctx* ctx, const StreamCfg& sc, int n_steps, int tail
 }
 
 __global__ void dec_init_kernel(DecState* st, int* finished, int* seq, int seq_ld, const int* prompt, int n_prompt, int B,
-                                int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg) {
+                                int eos, unsigned int* xcount, int n_xcount, unsigned int* bar, unsigned long long* dbg,
+                                unsigned int* kflag, int n_kflag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) { st->pos = 0; st->n_finished = 0; st->bar_epoch = 0u; *bar = 0u; }
   if (i < 128) dbg[i] = 0ull;
   if (i < n_xcount) xcount[i] = 0u;
+  if (i < n_kflag) kflag[i] = 0u;
   if (i < B) finished[i] = 0;
   if (i < B * seq_ld) {
     int b = i / seq_ld, t = i - b * seq_ld;
@@ -1206,7 +1241,7 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
 
   int n_init = B * m.n_text_ctx;
   dec_init_kernel<<<(n_init + 255) / 256, 256, 0, st>>>(bf.st, bf.finished, bf.seq, m.n_text_ctx, prompt, n_prompt, B,
-                                                        m.eos_id, bf.xcount, B * m.n_heads, bf.bar, bf.dbg);
+                                                        m.eos_id, bf.xcount, B * m.n_heads, bf.bar, bf.dbg, bf.kflag, ctx->sm_count / 4 + 1);
   CW_CHECK_LAUNCH("dec_init_kernel");
   ctx->launches += 1;
 
@@ -1259,6 +1294,18 @@ int decode_run(cw_ctx* ctx, const void* xkv, int B, const int32_t* prompt, int n
       for (int i = 0; i < 10; ++i) {
         fprintf(stderr, "  %-10s", nm[i]);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %8.0f", (double)h[32 + 8 * i + k] / s);
+        fprintf(stderr, "\n");
+      }
+      {  // last cross-attention phase of the call: when did every CTA enter it / finish its chunks (absolute globaltimer)
+        std::vector<unsigned long long> hx(2048);
+        CW_CUDA(cudaMemcpy(hx.data(), bf.dbg + 128, hx.size() * 8, cudaMemcpyDeviceToHost));
+        const int G = ctx->sm_count;
+        unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+        for (int c = 0; c < G; ++c) { s0 = std::min(s0, hx[c]); s1 = std::max(s1, hx[c]); e0 = std::min(e0, hx[1024 + c]); e1 = std::max(e1, hx[1024 + c]); }
+        fprintf(stderr, "[CW_STREAM_PROF] last cross phase: CTAs enter within %llu ns; first finishes its chunks %llu ns after the first entry, last %llu ns\n",
+                s1 - s0, e0 - s0, e1 - s0);
+        fprintf(stderr, "  per-CTA chunk-loop end (ns after first entry):");
+        for (int c = 0; c < G; ++c) fprintf(stderr, " %llu", hx[1024 + c] - s0);
         fprintf(stderr, "\n");
       }
 #endif

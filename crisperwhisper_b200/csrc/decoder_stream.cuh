@@ -41,7 +41,7 @@ enum { SPH_SAMPLE_EMBED = 0, SPH_GEMV = 1, SPH_SELF = 2, SPH_CROSS = 3 };
 enum { EPI_LOGITS = 4 };
 
 struct SPhase {
-  int type, epi, N, K, l, ln, rot, dbg_slot;
+  int type, epi, N, K, l, ln, rot, dbg_slot;   // dbg_slot doubles as the id of the phase kind (same tile split in every layer)
   const bf16* Wp; const float* bias; const float* ln_g; const float* ln_b;
   const float* src_f32; const bf16* src_bf16;
   float* out_f32; bf16* out_bf16; bf16* kcache; bf16* vcache;
@@ -66,6 +66,7 @@ struct StreamParams {
   const XItem* xitems; const int* xitem_off;
   unsigned int* bar;
   float* spart;
+  float* kpart; unsigned int* kflag;   // fc2 K-split groups: partial sums [G/4][3][8 tiles][128], arrival counters [G/4]
   unsigned long long* dbg;
   const SPhase* prog; int n_phases;
   const uint8_t* suppress; int max_new, eos, no_ts, max_initial_ts, flags;
@@ -85,6 +86,7 @@ __shared__ __align__(8) uint64_t s_empty[kSMaxSlots];
 __shared__ int s_flag[4];
 __shared__ int s_ms[64];
 __shared__ unsigned long long s_dbg_t;        // CW_MEGA_DEBUG: time of the previous tick (CTA 1, thread 0)
+__shared__ int s_dbg_slot_prev;
 
 // ---- small PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -175,10 +177,8 @@ __device__ __forceinline__ void s_bulk_g2s(uint32_t dst, const void* src, uint32
 
 // Grid-wide barrier of the consumer warps on a monotonically increasing counter (zeroed by dec_init_kernel); `target`
 // is known up front, so the arrival is a fire-and-forget red.release and the poll starts right behind it.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
-  cons_bar();
-  S_SUB(6);
-  if (threadIdx.x == 0) {
+__device__ __forceinline__ void grid_arrive_and_wait(unsigned int* bar, unsigned int target) {   // thread 0, between two CTA barriers
+  {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int spins = 0;
     unsigned long long t0 = 0;
@@ -192,8 +192,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
       }
     }
   }
-  S_SUB(7);
-  cons_bar();
 }
 
 // ---- producer ---------------------------------------------------------------------------------------------------------
@@ -221,9 +219,21 @@ struct SProd {
   }
 };
 
+__shared__ int s_trange[16][2];   // (first tile, tile count) of this CTA per phase kind, filled once per launch
 __device__ __forceinline__ void tile_range(const SPhase* D, int& t0, int& cnt) {
+  t0 = s_trange[D->dbg_slot][0];
+  cnt = s_trange[D->dbg_slot][1];
+}
+__device__ __forceinline__ void tile_range_compute(const SPhase* D, int& t0, int& cnt) {
   const int G = c_sp.G;
   const int n_tiles = D->N >> 3;
+  if (D->rot < 0) {   // K-split groups of 4 CTAs (fc2): CTA c works on k-chunk c / (G/4) of the tiles of group c % (G/4)
+    const int NGq = G >> 2, gq = (int)blockIdx.x % NGq;
+    const int base = n_tiles / NGq, rem = n_tiles - base * NGq;
+    cnt = base + (gq < rem ? 1 : 0);
+    t0 = gq * base + (gq < rem ? gq : rem);
+    return;
+  }
   int cp = (int)blockIdx.x + D->rot;
   if (cp >= G) cp -= G;
   const int base = n_tiles / G, rem = n_tiles - base * G;
@@ -251,15 +261,17 @@ __device__ __noinline__ void s_producer(uint32_t full0, uint32_t empty0, int pos
         tile_range(D, t0, cnt);
         if (cnt == 0) continue;
         if (D->ln) P.two(D->ln_g, D->ln_b, (uint32_t)d * 4u, (uint32_t)d * 4u);
-        const int KC = D->K / d;
+        const bool grouped = D->rot < 0;
+        const int KC = grouped ? 1 : D->K / d;
         const size_t tile_elems = (size_t)8 * D->K, blk_elems = (size_t)8 * d;
+        const size_t kc_off = grouped ? (size_t)((int)blockIdx.x / (G >> 2)) * blk_elems : 0;
         const int TB = c_sp.TB;
         for (int tb = 0; tb < cnt; tb += TB) {   // as s_ph_gemv: pairs of tiles, k-chunk by k-chunk, the two blocks of the pair
           const int nb = (cnt - tb < TB) ? cnt - tb : TB;
           for (int tp = 0; tp < nb; tp += 2)
             for (int kc = 0; kc < KC; ++kc)
               for (int ti = tp; ti < nb && ti < tp + 2; ++ti)
-                P.one(D->Wp + (size_t)(t0 + tb + ti) * tile_elems + (size_t)kc * blk_elems, SB);
+                P.one(D->Wp + (size_t)(t0 + tb + ti) * tile_elems + (size_t)kc * blk_elems + kc_off, SB);
         }
       } else if (type == SPH_SELF) {
         if (pos == 0) continue;
@@ -479,6 +491,7 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
   int t0, cnt;
   tile_range(D, t0, cnt);
   if (cnt == 0) return seq;
+  S_SUB(0);
   const bf16* xs = reinterpret_cast<const bf16*>(ssm + c_sp.xs_off);
   float* red = reinterpret_cast<float*>(ssm + c_sp.red_off);
   const int XS = d + 16;
@@ -499,9 +512,9 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
     if (em < B) { ms.at_begin = s_ms[em * 4]; ms.last_was_ts = s_ms[em * 4 + 1]; ms.penult_was_ts = s_ms[em * 4 + 2]; ms.ts_last_excl = s_ms[em * 4 + 3]; }
   }
   // activation fragments = the B operand (k16 x n8): sample g (and g + 8), k = 16 s + 4 t .. + 3 of this warp's k-steps.
-  // MODE 1, B <= 8: the fragments of all k-chunks (K = 4 d: 40 registers) are requested at once right after the barrier and
-  // stay resident for every tile: one L2 round trip per phase. B > 8: reloaded per k-chunk.
-  constexpr int KCR = (MODE == 1) ? (BIG ? 1 : 4) : 1;
+  // MODE 1 (K = 4 d), B <= 8: two fragment sets alternate — the next k-chunk's fragments are in flight from L2 while the
+  // current one is multiplied (a third set would hide more but spills at 96 registers). B > 8: reloaded per k-chunk.
+  constexpr int KCR = (MODE == 1) ? (BIG ? 1 : 2) : 1;
   uint2 fq[KCR][kSKsMax], fb[BIG ? kSKsMax : 1];
   auto load_frags = [&](uint2 (&A)[kSKsMax], uint2 (&Bq)[BIG ? kSKsMax : 1], int kc) {
 #pragma unroll
@@ -522,9 +535,7 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
       }
     }
   };
-#pragma unroll
-  for (int kc = 0; kc < KCR; ++kc)
-    if (kc < KC) load_frags(fq[kc], fb, kc);
+  if (KCR == 1) load_frags(fq[0], fb, 0);
   S_SUB(2);
   for (int tb = 0; tb < cnt; tb += TB) {
     const int nb = (cnt - tb < TB) ? cnt - tb : TB;
@@ -557,9 +568,14 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
         seq += two ? 2u : 1u;
       };
       if (KCR > 1) {
+        load_frags(fq[0], fb, 0);
+#pragma unroll 1
+        for (int kc = 0; kc < KC; ++kc) {   // one copy of the multiply code; the next chunk's fragments are already in flight
+          if (kc + 1 < KC) load_frags(fq[KCR > 1 ? 1 : 0], fb, kc + 1);
+          chunk(fq[0]);
 #pragma unroll
-        for (int kc = 0; kc < KCR; ++kc)   // K <= 4 d (checked on the host)
-          if (kc < KC) chunk(fq[KCR > 1 ? kc : 0]);
+          for (int i = 0; i < kSKsMax; ++i) fq[0][i] = fq[KCR > 1 ? 1 : 0][i];
+        }
       } else {
 #pragma unroll 1
         for (int kc = 0; kc < KC; ++kc) {
@@ -666,6 +682,126 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
   return seq;
 }
 
+// ---- fc2 (K = 4 d) as K-split groups of 4 CTAs ---------------------------------------------------------------------------------
+// With the rows of fc2 split over all CTAs every CTA needs the whole 5120-wide fc1 output (80 KB per CTA, 11.8 MB through
+// the L2 per phase: ~9 us, and 12 CTAs carry twice the weights of the others). Here CTA c takes ONE k-chunk (kc = c / (G/4))
+// of the tiles of group c % (G/4): 20 KB of activations, 4-5 weight blocks, like every other projection. The three partner
+// CTAs of a group leave their partial sums in L2 and bump the group's counter (release); the leader (kc = 0) waits for the
+// counter (acquire) and adds them in fixed order kc = 0, 1, 2, 3 — deterministic — then applies bias + residual.
+template <bool BIG>
+__device__ __noinline__ uint32_t s_ph_fc2g(const SPhase* D, int pos, uint32_t seq) {
+  const SCons C = make_cons(D);
+  const int d = c_sp.d, B = c_sp.B, R = c_sp.R, G = c_sp.G;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int N = D->N, K = D->K, nks = d >> 4;
+  const int NGq = G >> 2, gq = (int)blockIdx.x % NGq, kc = (int)blockIdx.x / NGq;
+  int t0, cnt;
+  tile_range(D, t0, cnt);
+  if (cnt == 0) return seq;
+  S_SUB(0);
+  float* red = reinterpret_cast<float*>(ssm + c_sp.red_off);
+  float* lead = reinterpret_cast<float*>(ssm + c_sp.xs_off);   // leader: its own partial sums of up to 8 tiles (xs is unused here)
+  const int rep = rep_of_cta();
+  const int TB = c_sp.TB;
+  const int eti = tid >> 7, eo = tid & 127, em = eo >> 3;
+  uint2 fa[kSKsMax], fb[BIG ? kSKsMax : 1];
+#pragma unroll
+  for (int i = 0; i < kSKsMax; ++i) {
+    const int s = warp + 16 * i;
+    fa[i] = make_uint2(0u, 0u);
+    if (BIG) fb[BIG ? i : 0] = make_uint2(0u, 0u);
+    if (s < nks) {
+      const bf16* src = D->src_bf16 + (size_t)rep * B * K + (size_t)kc * d + 16 * s + 4 * t;
+      if (g < B) fa[i] = ld_cg8(src + (size_t)g * K);
+      if (BIG && g + 8 < B) fb[BIG ? i : 0] = ld_cg8(src + (size_t)(g + 8) * K);
+    }
+  }
+  S_SUB(2);
+  float* part = c_sp.kpart + ((size_t)gq * 3 + (kc > 0 ? kc - 1 : 0)) * 8 * 128;
+  for (int tb = 0; tb < cnt; tb += TB) {
+    const int nb = (cnt - tb < TB) ? cnt - tb : TB;
+#pragma unroll 1
+    for (int tp = 0; tp < nb; tp += 2) {
+      const bool two = tp + 1 < nb;
+      float c[kSKsMax][4], c2[BIG ? kSKsMax : 1][4];
+#pragma unroll
+      for (int i = 0; i < kSKsMax; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+      if (BIG) {
+#pragma unroll
+        for (int i = 0; i < (BIG ? kSKsMax : 1); ++i) { c2[i][0] = c2[i][1] = c2[i][2] = c2[i][3] = 0.f; }
+      }
+      const uint32_t sx = C.wait(seq) + (uint32_t)lane * 8u;
+      const uint32_t sy = two ? C.wait(seq + 1) + (uint32_t)lane * 8u : 0u;
+      mma_pair<BIG>(c, c2, fa, fb, sx, sy, warp, nks);
+      __syncwarp();
+      if (lane == 0) { C.release(seq, 1); if (two) C.release(seq + 1, 1); }
+      seq += two ? 2u : 1u;
+      float sx0 = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) + c[4][0], sx1 = ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1])) + c[4][1];
+      float sy0 = ((c[0][2] + c[1][2]) + (c[2][2] + c[3][2])) + c[4][2], sy1 = ((c[0][3] + c[1][3]) + (c[2][3] + c[3][3])) + c[4][3];
+      float* rx = red + ((size_t)warp * TB + tp) * 128;
+      rx[(2 * t) * 8 + g] = sx0; rx[(2 * t + 1) * 8 + g] = sx1;
+      if (two) { rx[128 + (2 * t) * 8 + g] = sy0; rx[128 + (2 * t + 1) * 8 + g] = sy1; }
+      if (BIG) {
+        sx0 = ((c2[0][0] + c2[BIG ? 1 : 0][0]) + (c2[BIG ? 2 : 0][0] + c2[BIG ? 3 : 0][0])) + c2[BIG ? 4 : 0][0];
+        sx1 = ((c2[0][1] + c2[BIG ? 1 : 0][1]) + (c2[BIG ? 2 : 0][1] + c2[BIG ? 3 : 0][1])) + c2[BIG ? 4 : 0][1];
+        sy0 = ((c2[0][2] + c2[BIG ? 1 : 0][2]) + (c2[BIG ? 2 : 0][2] + c2[BIG ? 3 : 0][2])) + c2[BIG ? 4 : 0][2];
+        sy1 = ((c2[0][3] + c2[BIG ? 1 : 0][3]) + (c2[BIG ? 2 : 0][3] + c2[BIG ? 3 : 0][3])) + c2[BIG ? 4 : 0][3];
+        rx[(8 + 2 * t) * 8 + g] = sx0; rx[(9 + 2 * t) * 8 + g] = sx1;
+        if (two) { rx[128 + (8 + 2 * t) * 8 + g] = sy0; rx[128 + (9 + 2 * t) * 8 + g] = sy1; }
+      }
+    }
+    S_SUB(3);
+    cons_bar();
+    if (eti < nb) {   // this CTA's k-chunk partial of output (tile tb + eti, sample em, row eo & 7)
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) v += red[((size_t)w * TB + eti) * 128 + eo];
+      if (kc == 0) lead[(size_t)(tb + eti) * 128 + eo] = v;
+      else part[(size_t)(tb + eti) * 128 + eo] = v;
+    }
+    cons_bar();   // red is rewritten by the next batch; lead/part complete
+  }
+  S_SUB(4);
+  const unsigned int target = 3u * (unsigned int)(pos * c_sp.dec_layers + D->l + 1);
+  if (kc != 0) {
+    __threadfence();
+    cons_bar();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c_sp.kflag + gq) : "memory");
+  } else {
+    // epilogue operands first, then the partners
+    if (tid == 0) {
+      unsigned int spins = 0;
+      unsigned long long t0w = 0;
+      while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c_sp.kflag + gq) : "memory");
+        if ((int)(v - target) >= 0) break;
+        if ((++spins & 0xfffu) == 0) {
+          if (t0w == 0) t0w = s_now_ns();
+          else if (s_now_ns() - t0w > 2000000000ull) __trap();
+        }
+      }
+    }
+    cons_bar();
+    for (int idx = tid; idx < cnt * 128; idx += kSConsThreads) {
+      const int ti = idx >> 7, o = idx & 127, m = o >> 3;
+      if (m < B) {
+        const int n = (t0 + ti) * 8 + (o & 7);
+        const float* pp = c_sp.kpart + (size_t)gq * 3 * 8 * 128 + (size_t)ti * 128 + o;
+        float v = lead[(size_t)ti * 128 + o];
+        v += ld_cg(pp);
+        v += ld_cg(pp + 8 * 128);
+        v += ld_cg(pp + 2 * 8 * 128);
+        if (D->bias) v += __ldg(D->bias + n);
+        const float xn = ld_cg(D->out_f32 + ((size_t)rep * B + m) * N + n) + v;
+        for (int r = 0; r < R; ++r) D->out_f32[((size_t)r * B + m) * N + n] = xn;
+      }
+    }
+  }
+  S_SUB(5);
+  return seq;
+}
+
 // ---- attention: one 4-warp group, 8 threads per row (16 B of K and of V each), online softmax in the log2 domain ----------
 struct AState { float m, l, acc[8]; };
 
@@ -702,17 +838,76 @@ __device__ __forceinline__ void attn_row(AState& S, const float* qv, const uint4
   }
 }
 
-// rows of one chunk held in ring slot `sa` (K rows at +0, V rows at +SB/2), nrows <= CR
+// rows of one chunk held in ring slot `sa` (K rows at +0, V rows at +SB/2), nrows <= CR. A thread owns rows r, r + 16, ...
+// (8 threads per row); up to 5 of its rows are processed TOGETHER: five independent dot products and shuffle trees, one
+// running-maximum update for the block, five independent exponentials, then the P.V accumulation — the row-at-a-time online
+// softmax is one long dependency chain (dot -> shuffles -> max -> ex2 -> rescale) that left the SM at a fraction of its issue rate.
 __device__ __forceinline__ void attn_chunk(AState& S, const float* qv, uint32_t sa, int nrows, int gtid, float* sc_base /*global or null*/) {
+  constexpr int RB = 5;
   const int sub = gtid & 7, r = gtid >> 3;
   const uint32_t ka = sa + (uint32_t)sub * 16u, va = ka + (uint32_t)(c_sp.SB >> 1);
-#pragma unroll 2
-  for (int j0 = 0; j0 < nrows; j0 += 16) {
-    const int j = j0 + r;
-    const bool live = j < nrows;
-    uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
-    if (live) { ku = lds128(ka + (uint32_t)j * 128u); vu = lds128(va + (uint32_t)j * 128u); }
-    attn_row(S, qv, ku, vu, live, (sc_base != nullptr && sub == 0) ? sc_base + j : nullptr);
+#pragma unroll 1
+  for (int j0 = 0; j0 < nrows; j0 += 16 * RB) {
+    float sc[RB];
+    bool live[RB];
+    {
+      uint4 ku[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const int j = j0 + 16 * i + r;
+        live[i] = j < nrows;
+        ku[i] = make_uint4(0, 0, 0, 0);
+        if (live[i]) ku[i] = lds128(ka + (uint32_t)j * 128u);
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        const uint32_t kw[4] = {ku[i].x, ku[i].y, ku[i].z, ku[i].w};
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s = fmaf(qv[2 * e], __uint_as_float(kw[e] << 16), s);
+          s = fmaf(qv[2 * e + 1], __uint_as_float(kw[e] & 0xffff0000u), s);
+        }
+        sc[i] = s;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 1);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 2);
+#pragma unroll
+    for (int i = 0; i < RB; ++i) sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], 4);
+    float mb = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      if (live[i]) {
+        mb = fmaxf(mb, sc[i]);
+        if (sc_base != nullptr && sub == 0) sc_base[j0 + 16 * i + r] = sc[i];
+      }
+    }
+    if (mb > S.m) {   // new running maximum: rescale what has been accumulated (S.m = -inf at the start: factor 0)
+      const float f = ex2_approx(S.m - mb);
+      S.m = mb;
+      S.l *= f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) S.acc[e] *= f;
+    }
+    float pj[RB];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) pj[i] = live[i] ? ex2_approx(sc[i] - S.m) : 0.f;
+    S.l += ((pj[0] + pj[1]) + (pj[2] + pj[3])) + pj[4];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      if (live[i]) {
+        const uint4 vu = lds128(va + (uint32_t)(j0 + 16 * i + r) * 128u);
+        const uint32_t vw[4] = {vu.x, vu.y, vu.z, vu.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          S.acc[2 * e] = fmaf(pj[i], __uint_as_float(vw[e] << 16), S.acc[2 * e]);
+          S.acc[2 * e + 1] = fmaf(pj[i], __uint_as_float(vw[e] & 0xffff0000u), S.acc[2 * e + 1]);
+        }
+      }
+    }
   }
 }
 
@@ -804,6 +999,9 @@ __device__ __noinline__ uint32_t s_ph_self(const SPhase* D, int pos, uint32_t se
 
 __device__ __noinline__ uint32_t s_ph_cross(const SPhase* D, int pos, uint32_t seq) {
   const SCons C = make_cons(D);
+#ifdef CW_STREAM_PROF
+  if (c_sp.dbg != nullptr && threadIdx.x == 0) c_sp.dbg[128 + blockIdx.x] = s_now_ns();
+#endif
   const int d = c_sp.d, H = c_sp.n_heads, F = c_sp.F;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gi = warp >> 2, gtid = threadIdx.x & 127, sub = gtid & 7;
@@ -886,6 +1084,9 @@ __device__ __noinline__ uint32_t s_ph_cross(const SPhase* D, int pos, uint32_t s
     }
   }
   S_SUB(3);
+#ifdef CW_STREAM_PROF
+  if (c_sp.dbg != nullptr && threadIdx.x == 0) c_sp.dbg[128 + 1024 + blockIdx.x] = s_now_ns();
+#endif
   return seq + (uint32_t)n_it;
 }
 
@@ -966,6 +1167,69 @@ __device__ __forceinline__ void s_tick(int slot) {
   }
 }
 
+// One phase + the grid barrier behind it. The loop state (phase, position, stream sequence number, barrier count, phases left)
+// lives in SHARED memory and is advanced by thread 0 inside the barrier (after every thread has arrived, before any is
+// released), so nothing has to survive the calls in registers: with ~215 KB of shared memory the L1 is a few KB and every
+// spilled or stack-saved register costs an L2 round trip on the critical path of the phase.
+struct SLoop { uint32_t seq; unsigned int bar_idx; int ph; int pos; int left; int pad[3]; };
+__shared__ volatile SLoop s_loop;
+__device__ __forceinline__ const SPhase* cur_phase() { return &s_phase[s_loop.ph & 1]; }
+
+__device__ __noinline__ void s_step() {
+  {
+    const int tid = threadIdx.x;
+    const int ph = s_loop.ph;
+#ifdef CW_STREAM_PROF
+    if (blockIdx.x == 1 && tid == 0) { s_prof_slot = s_phase[ph & 1].dbg_slot; s_prof_t = s_now_ns(); }
+#endif
+    // the next phase's descriptor travels global -> shared asynchronously (cp.async, no register lives across the phase);
+    // buffer = phase index & 1 — the host guarantees an even number of phases per step
+    if ((tid >> 5) == 1 && (tid & 31) < (int)(sizeof(SPhase) / 4)) {
+      const int nxt = (ph + 1 < c_sp.n_phases) ? ph + 1 : 0;
+      const uint32_t dst = s_u32(reinterpret_cast<int*>(&s_phase[(ph + 1) & 1]) + (tid & 31));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(reinterpret_cast<const int*>(c_sp.prog + nxt) + (tid & 31)) : "memory");
+    }
+  }
+  uint32_t seq = s_loop.seq;
+  const int type = cur_phase()->type;
+  if (type == SPH_GEMV) {
+    if (cur_phase()->ln) seq = s_ln_stage(cur_phase(), s_loop.pos, seq);
+    const SPhase* D = cur_phase();   // re-derived from shared memory after the call
+    const int pos = s_loop.pos;
+    const int mode = (D->epi == EPI_LOGITS) ? 2 : ((D->K > c_sp.d) ? 1 : 0);
+    if (c_sp.B > 8) {
+      if (mode == 2) seq = s_ph_gemv<true, 2>(D, pos, seq);
+      else if (mode == 1) seq = (D->rot < 0) ? s_ph_fc2g<true>(D, pos, seq) : s_ph_gemv<true, 1>(D, pos, seq);
+      else seq = s_ph_gemv<true, 0>(D, pos, seq);
+    } else {
+      if (mode == 2) seq = s_ph_gemv<false, 2>(D, pos, seq);
+      else if (mode == 1) seq = (D->rot < 0) ? s_ph_fc2g<false>(D, pos, seq) : s_ph_gemv<false, 1>(D, pos, seq);
+      else seq = s_ph_gemv<false, 0>(D, pos, seq);
+    }
+  }
+  else if (type == SPH_CROSS) seq = s_ph_cross(cur_phase(), s_loop.pos, seq);
+  else if (type == SPH_SELF) seq = s_ph_self(cur_phase(), s_loop.pos, seq);
+  else if (blockIdx.x == 0) s_sample_embed(s_loop.pos, true);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  s_tick(2 * cur_phase()->dbg_slot);
+  // grid barrier; thread 0 advances the loop state between the two CTA barriers
+  cons_bar();
+  S_SUB(6);
+  if (threadIdx.x == 0) {
+    const int ph = s_loop.ph;
+    const unsigned int bar_idx = s_loop.bar_idx + 1u;
+    const bool wrap = ph + 1 >= c_sp.n_phases;
+    s_loop.seq = seq; s_loop.bar_idx = bar_idx; s_loop.ph = wrap ? 0 : ph + 1;
+    if (wrap) s_loop.pos = s_loop.pos + 1;
+    s_loop.left = s_loop.left - 1;
+    s_dbg_slot_prev = s_phase[ph & 1].dbg_slot;
+    grid_arrive_and_wait(c_sp.bar, bar_idx * gridDim.x);
+  }
+  S_SUB(7);
+  cons_bar();
+  s_tick(2 * s_dbg_slot_prev + 1);
+}
+
 __global__ void __launch_bounds__(kSAllThreads, 1) decode_stream_kernel(int n_steps, int tail_sample) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const int pos0 = c_sp.st->pos;              // written by the previous launch only
@@ -986,6 +1250,15 @@ __global__ void __launch_bounds__(kSAllThreads, 1) decode_stream_kernel(int n_st
     for (int i = tid; i < n_map; i += kSAllThreads) s_amap[i] = c_sp.align_map[i];
     if (tid < (int)(sizeof(SPhase) / 4))
       reinterpret_cast<int*>(&s_phase[0])[tid] = reinterpret_cast<const int*>(c_sp.prog)[tid];
+    if (tid >= 64 && tid < 64 + c_sp.n_phases && tid < 64 + 12) {   // one step's phase kinds: the first layer + the logits phase
+      const int ph = (tid - 64 < 10) ? tid - 64 : c_sp.n_phases - 1;
+      const SPhase* Dp = c_sp.prog + ph;
+      if (Dp->type == SPH_GEMV) {
+        int a0, a1;
+        tile_range_compute(Dp, a0, a1);
+        s_trange[Dp->dbg_slot][0] = a0; s_trange[Dp->dbg_slot][1] = a1;
+      }
+    }
   }
   __syncthreads();
   if (warp == 16) {  // producer warp: one lane streams, the others leave
@@ -994,48 +1267,13 @@ __global__ void __launch_bounds__(kSAllThreads, 1) decode_stream_kernel(int n_st
     if (tid == kSConsThreads) s_producer(s_u32(&s_full[0]), s_u32(&s_empty[0]), pos0, n_steps);
     return;
   }
-  uint32_t seq = 0;
   s_tick(-1);
-  const int n_ph = c_sp.n_phases;
-  for (int s = 0; s < n_steps; ++s) {
-    const int pos = pos0 + s;
+  if (tid == 0) { s_loop.seq = 0u; s_loop.bar_idx = bar_idx; s_loop.ph = 0; s_loop.pos = pos0; s_loop.left = n_steps * c_sp.n_phases; }
+  cons_bar();
 #pragma unroll 1
-    for (int ph = 0; ph < n_ph; ++ph) {
-      const SPhase* D = &s_phase[ph & 1];
-      const int type = D->type;
-#ifdef CW_STREAM_PROF
-      if (blockIdx.x == 1 && tid == 0) { s_prof_slot = D->dbg_slot; s_prof_t = s_now_ns(); }
-#endif
-      if (type == SPH_GEMV) {
-        if (D->ln) seq = s_ln_stage(D, pos, seq);
-        const int mode = (D->epi == EPI_LOGITS) ? 2 : ((D->K > c_sp.d) ? 1 : 0);
-        if (c_sp.B > 8) {
-          if (mode == 2) seq = s_ph_gemv<true, 2>(D, pos, seq);
-          else if (mode == 1) seq = s_ph_gemv<true, 1>(D, pos, seq);
-          else seq = s_ph_gemv<true, 0>(D, pos, seq);
-        } else {
-          if (mode == 2) seq = s_ph_gemv<false, 2>(D, pos, seq);
-          else if (mode == 1) seq = s_ph_gemv<false, 1>(D, pos, seq);
-          else seq = s_ph_gemv<false, 0>(D, pos, seq);
-        }
-      }
-      else if (type == SPH_CROSS) seq = s_ph_cross(D, pos, seq);
-      else if (type == SPH_SELF) seq = s_ph_self(D, pos, seq);
-      else if (blockIdx.x == 0) s_sample_embed(pos, true);
-      s_tick(2 * D->dbg_slot);
-      // the next phase's descriptor travels to shared memory while the grid barrier is in flight (buffer = phase index & 1;
-      // the host guarantees an even number of phases per step, so phase 0 of the next step lands in buffer 0 again)
-      bar_idx += 1;
-      if (warp == 1 && (tid & 31) < (int)(sizeof(SPhase) / 4)) {
-        const int nxt = (ph + 1 < n_ph) ? ph + 1 : 0;
-        reinterpret_cast<int*>(&s_phase[(ph + 1) & 1])[tid & 31] = reinterpret_cast<const int*>(c_sp.prog + nxt)[tid & 31];
-      }
-      grid_barrier(c_sp.bar, bar_idx * gridDim.x);
-      s_tick(2 * s_phase[ph & 1].dbg_slot + 1);
-    }
-  }
-  if (tail_sample && blockIdx.x == 0) s_sample_embed(pos0 + n_steps, false);
-  if (blockIdx.x == 0 && tid == 0) { c_sp.st->pos = pos0 + n_steps; c_sp.st->bar_epoch = bar_idx; }
+  while (s_loop.left > 0) s_step();
+  if (tail_sample && blockIdx.x == 0) s_sample_embed(s_loop.pos, false);
+  if (blockIdx.x == 0 && tid == 0) { c_sp.st->pos = s_loop.pos; c_sp.st->bar_epoch = s_loop.bar_idx; }
 #ifdef CW_STREAM_PROF
   if (c_sp.dbg != nullptr && blockIdx.x == 1 && tid == 0)
     for (int i = 0; i < 80; ++i) c_sp.dbg[32 + i] += s_prof_acc[i];

@@ -49,16 +49,16 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 def test_cross_attention_plan_covers_and_balances():
     """cw_decode_cross_plan (host-only): the step kernel's cross-attention stream plan. Every (sample, head) task's frames
-    are covered exactly once by chunks of <= chunk_rows frames; the chunks of a task inside one consumer group form one
-    segment (first/last flags, consecutive segment indices, splits = number of segments); every group of every CTA gets the
-    same number of chunks +-1 and a CTA's items are issued round-robin over its groups. At the bench shape (160 tasks x 1500
-    frames, 80-row chunks, 148 CTAs) every CTA streams 20 or 21 chunks."""
+    are covered exactly once by chunks of <= chunk_rows frames; a task is cut into splits[t] contiguous segments, every
+    segment belongs to exactly one consumer group (first/last flags on its first/last chunk, consecutive segment indices),
+    and while tasks <= 4 x n_cta every group owns exactly one segment. At the bench shape (160 tasks x 1500 frames, 80-row
+    chunks, 148 CTAs) every CTA streams 20 or 21 chunks and a task has 3 or 4 segments."""
     import ctypes as C
     import numpy as np
     from crisperwhisper_b200 import _lib as L
     lib = L.load()
     for tasks, F, cr, n_cta in ((160, 1500, 80, 148), (6, 1500, 8, 148), (100, 1500, 80, 132), (320, 1500, 80, 148),
-                                (1, 1500, 80, 1), (3, 37, 8, 5)):
+                                (1, 1500, 80, 1), (3, 37, 8, 5), (640, 1500, 80, 148)):
         cpt = -(-F // cr)
         items = np.full((tasks * cpt, 6), -7, dtype=np.int32)
         off = np.zeros(n_cta + 1, dtype=np.int32)
@@ -69,19 +69,13 @@ def test_cross_attention_plan_covers_and_balances():
         assert off[0] == 0 and off[-1] == tasks * cpt and (np.diff(off) >= 0).all()
         cover = np.zeros((tasks, F), dtype=np.int32)
         segs = {}
-        per_group = np.zeros((n_cta, 4), dtype=np.int64)
+        group_segs = {}
         for c in range(n_cta):
-            mine = items[off[c]:off[c + 1]]
-            seen = [0, 0, 0, 0]
-            last_round = -1
-            for t, f0, nf, g, sg, fl in mine:
+            for t, f0, nf, g, sg, fl in items[off[c]:off[c + 1]]:
                 assert 0 <= t < tasks and 0 < nf <= cr and f0 % cr == 0 and f0 + nf <= F and 0 <= g < 4
                 cover[t, f0:f0 + nf] += 1
-                per_group[c, g] += 1
-                # round-robin issue order: the k-th item of a group never comes before the k-th item of a lower group
-                assert seen[g] >= last_round or True
-                seen[g] += 1
                 segs.setdefault((t, sg), []).append((c, g, f0, nf, fl))
+                group_segs.setdefault((c, g), set()).add((t, sg))
         assert (cover == 1).all()
         for t in range(tasks):
             assert sorted(sg for (tt, sg) in segs if tt == t) == list(range(splits[t]))
@@ -90,11 +84,11 @@ def test_cross_attention_plan_covers_and_balances():
             f = [x[2] for x in lst]
             assert f == sorted(f) and all(f[i + 1] == f[i] + lst[i][3] for i in range(len(f) - 1))   # contiguous frames
             assert lst[0][4] & 1 and lst[-1][4] & 2 and all(not (x[4] & 1) for x in lst[1:]) and all(not (x[4] & 2) for x in lst[:-1])
-        flat = per_group.reshape(-1)
-        assert flat.max() - flat.min() <= 1
+        if tasks <= 4 * n_cta:
+            assert max(len(v) for v in group_segs.values()) == 1               # one segment, one finalisation per group
         if (tasks, n_cta) == (160, 148):
             per_cta = np.diff(off)
-            assert per_cta.min() == 20 and per_cta.max() == 21 and splits.max() <= 5
+            assert per_cta.min() == 20 and per_cta.max() == 21 and set(np.unique(splits)) == {3, 4}
     bad = np.zeros((10, 6), dtype=np.int32)
     assert lib.cw_decode_cross_plan(100, 1500, 0, 10, bad.ctypes.data_as(C.c_void_p), bad.ctypes.data_as(C.c_void_p),
                                     bad.ctypes.data_as(C.c_void_p)) != 0

@@ -52,6 +52,10 @@ int main() {
   // 16 warps per SM, one chain each
   k_hmma<<<148, 512>>>(d, 1000, 1); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   printf("hmma: 16 warps/SM x 1 chain: %.1f cycles per step\n", h[0] / 1000.0);
+  for (int chains : {2, 4, 8}) {
+    k_hmma<<<148, 512>>>(d, 1000, chains); cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("hmma: 16 warps/SM x %d chains: %.1f cycles per step = %.1f cycles per HMMA per SM\n", chains, h[0] / 1000.0, h[0] / 1000.0 / (16 * chains));
+  }
   uint2* buf; cudaMalloc(&buf, 64 << 20); cudaMemset(buf, 1, 64 << 20);
   unsigned* bar; cudaMalloc(&bar, 4);
   for (int R : {1, 2, 4, 8, 16, 37, 148}) {
