@@ -4,9 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (libcrisper.so kernels)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own path: HF pipeline on the host CPU
 
-Workload (BASELINE.json configs[1]): batch = 8 x 30 s synthetic 16 kHz chunks per GPU, CrisperWhisper-large-v3-shaped
-random-init weights, greedy decode of a FIXED, STATED number of new tokens (EOS suppressed so both arms do identical
-work — RTFx is proportional to 1/T in the HBM-bound decode), 20 alignment heads, median 7, DTW.
+Workload: one GPU = BASELINE.json configs[1] (batch = 8 x 30 s synthetic 16 kHz chunks); several GPUs = configs[3]'s share
+(32 chunks per GPU, round-robin, decode batches of 16, transcript all_gather inside the timed region).  CrisperWhisper-
+large-v3-shaped random-init weights, greedy decode of a FIXED, STATED number of new tokens (EOS suppressed so both arms do
+identical work — RTFx is proportional to 1/T in the decode), 20 alignment heads, median 7, DTW.  `stages` carries configs[2]
+(10 min clip), configs[4] (1024-utterance DTW, sharded over the ranks), the whole-encoder tensor roofline and the other
+decode batch.
 A step = one pass of the whole hot path (log-mel -> encoder -> cross-K/V -> greedy decode -> normalise/median/DTW) over
 one batch.  `value` = device-timed throughput with the waveforms already resident in HBM; `e2e` = the same metric
 through the public `pipeline(...)` call with HOST numpy waveforms in and the {"text","chunks"} dict out.
@@ -174,19 +177,31 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def traffic_from_profile():
+    """DRAM bytes of one launch of the dominant kernel, read from the committed ncu summary of this round (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r02_decode_stream_ncu.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    return d, os.path.relpath(p, ROOT)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="crisper", choices=["crisper", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="30 s chunks per GPU per step (BASELINE cfg 2: 8)")
+    ap.add_argument("--chunks-per-gpu", dest="chunks", type=int, default=0,
+                    help="30 s chunks per GPU per step; default 8 on one GPU (BASELINE cfg 2), 32 on several (cfg 4: 256 chunks over 8 GPUs)")
+    ap.add_argument("--batch", type=int, default=0, help="decode batch (chunks per cw_decode_greedy call); default 8 (cfg 2) / 16 (cfg 4 share)")
     ap.add_argument("--new-tokens", dest="new_tokens", type=int, default=445, help="decoded tokens per chunk (445 = n_text_ctx - prompt)")
-    ap.add_argument("--ref-tokens", dest="ref_tokens", type=int, default=8, help="decode length of the bounded CPU sample")
+    ap.add_argument("--ref-tokens", dest="ref_tokens", type=int, default=32, help="decode length of the bounded CPU sample")
     ap.add_argument("--ref-threads", dest="ref_threads", type=int, default=16, help="host threads for the reference arm")
     ap.add_argument("--ref-warmup", dest="ref_warmup", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the per-stage microbenchmarks")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-stage / per-config measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -209,8 +224,8 @@ def main():
         dist.barrier()
     from crisperwhisper_b200 import _lib as L
     from crisperwhisper_b200 import distributed as D
-    from crisperwhisper_b200 import generate as G
     from crisperwhisper_b200 import weights as Wt
+    from crisperwhisper_b200 import adjust_pauses_for_hf_pipeline_output
     from crisperwhisper_b200.engine import Engine
     from crisperwhisper_b200.asr_pipeline import mel_filters_slaney, pipeline
 
@@ -218,7 +233,6 @@ def main():
     dev = eng.device
     cfg = Wt.large_v3_config(n_align_heads=20, median_filter_width=7)
     cfg["suppress_tokens"] = [50257] + list(range(50366, 51866))  # same fixed-length, single-pass decode as the reference arm
-    t0 = time.perf_counter()
     pw = Wt.synthetic_weights(cfg, dev, seed=0) if rank == 0 else None
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -226,23 +240,13 @@ def main():
     torch.cuda.synchronize()
     bcast_ms = (time.perf_counter() - t1) * 1000.0
     eng.load_weights(pw)
-    B, T = args.batch, args.new_tokens
+    T = args.new_tokens
+    NC = args.chunks or (8 if world == 1 else 32)          # chunks per GPU per step
+    Bd = args.batch or (8 if NC <= 8 else 16)              # decode batch
     n_prompt = 3
     filt = torch.from_numpy(mel_filters_slaney(128)).to(dev)
-    waves_host = [synth_wave(rank * B + i) for i in range(B)]          # chunk i -> rank i mod W layout of cfg 4
-    wave_dev = torch.from_numpy(np.stack(waves_host)).to(dev)
-    prompt = torch.tensor([[50258, 50259, 50360]] * B, dtype=torch.int32, device=dev)
     flags = L.CW_DEC_SUPPRESS_EOS
-
-    def step_device():
-        """The hot path with inputs resident in HBM."""
-        _, tm, frames = eng.logmel(wave_dev, filt, None, want_f32=False, want_tm=True)
-        xkv, _ = eng.encode(tm)
-        out = eng.decode(xkv, prompt, T, flags=flags)
-        T_len = torch.full((B,), T - 1, dtype=torch.int32, device=dev)
-        F_len = torch.full((B,), 1500, dtype=torch.int32, device=dev)
-        jump = eng.align(out["align"], T_len, F_len, 7)
-        return out, jump
+    peaks = measured_peaks()
 
     def barrier():
         torch.cuda.synchronize()
@@ -250,81 +254,142 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_chunks(wave_dev, bd, tnew, gather):
+        """stages 1-3 over the resident waveforms [n, 480000] in decode batches of bd; with `gather`, the transcripts'
+        device records are all-gathered at the end (cfg 4's end collective) on the engine stream."""
+        outs = []
+        for b0 in range(0, wave_dev.shape[0], bd):
+            w = wave_dev[b0:b0 + bd]
+            nb = w.shape[0]
+            _, tm, _ = eng.logmel(w, filt, None, want_f32=False, want_tm=True)
+            xkv, _ = eng.encode(tm)
+            prompt = torch.tensor([[50258, 50259, 50360]] * nb, dtype=torch.int32, device=dev)
+            out = eng.decode(xkv, prompt, tnew, flags=flags)
+            jump = eng.align(out["align"], torch.full((nb,), tnew - 1, dtype=torch.int32, device=dev),
+                             torch.full((nb,), 1500, dtype=torch.int32, device=dev), 7)
+            outs.append((out["tokens"], jump))
+        if gather and world > 1:
+            with torch.cuda.stream(eng.stream):
+                toks = torch.cat([o[0] for o in outs]).contiguous()
+                jmp = torch.cat([o[1] for o in outs]).contiguous()
+                gt = [torch.empty_like(toks) for _ in range(world)]
+                gj = [torch.empty_like(jmp) for _ in range(world)]
+                dist.all_gather(gt, toks)
+                dist.all_gather(gj, jmp)
+        return outs
+
+    def time_device(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(eng.stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / steps)
+
+    # ---- headline: device-timed step -----------------------------------------------------------------------------------
+    waves_host = [synth_wave(i * world + rank) for i in range(NC)]            # chunk i -> rank i mod W (cfg 4 layout)
+    wave_dev = torch.from_numpy(np.stack(waves_host)).to(dev)
     for _ in range(max(args.warmup, 3)):
-        step_device()
+        run_chunks(wave_dev, Bd, T, gather=True)
     barrier()
     launches0 = eng.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(eng.stream):
-        ev0.record(eng.stream)
+    ev0.record(eng.stream)
     for _ in range(args.steps):
-        out, jump = step_device()
-    with torch.cuda.stream(eng.stream):
-        ev1.record(eng.stream)
+        run_chunks(wave_dev, Bd, T, gather=True)
+    ev1.record(eng.stream)
     barrier()
     clocks = sampler.stop()
     gpu_launches = eng.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    t_ms = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t_ms.item()) / args.steps
-    audio_s = 30.0 * B * world
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    audio_s = 30.0 * NC * world
     value = audio_s / (ms_per_step / 1000.0)
 
-    # secondary, clearly-labelled measurement at a typical speech decode length (30 s of speech is ~100-150 tokens)
-    alt = None
-    if T != 128 and not args.no_extras:
-        T2, prompt2 = 128, prompt
-
-        def step_alt():
-            _, tm2, _ = eng.logmel(wave_dev, filt, None, want_f32=False, want_tm=True)
-            xkv2, _ = eng.encode(tm2)
-            o2 = eng.decode(xkv2, prompt2, T2, flags=flags)
-            eng.align(o2["align"], torch.full((B,), T2 - 1, dtype=torch.int32, device=dev), torch.full((B,), 1500, dtype=torch.int32, device=dev), 7)
-        step_alt()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(eng.stream)
-        for _ in range(2):
-            step_alt()
-        a1.record(eng.stream)
-        barrier()
-        t_alt = torch.tensor([a0.elapsed_time(a1) / 2], device=dev)
-        if world > 1:
-            dist.all_reduce(t_alt, op=dist.ReduceOp.MAX)
-        alt = {"new_tokens": T2, "ms_per_step": round(float(t_alt.item()), 2), "value": round(audio_s / (float(t_alt.item()) / 1000.0), 1),
-               "note": "same workload with 128 new tokens per chunk (typical for 30 s of speech); not the headline"}
-
-    # ---- e2e through the public API: host numpy in, {"text","chunks"} out ------------------------------------
+    # ---- e2e through the public API: host numpy in, {"text","chunks"} out on rank 0 -----------------------------------------
     tok = big_tokenizer(cfg)
     pipe = pipeline("automatic-speech-recognition", model=eng, tokenizer=tok, feature_extractor=None, chunk_length_s=30,
-                    batch_size=B, return_timestamps="word")
+                    batch_size=Bd, return_timestamps="word")
     gk = {"max_new_tokens": T}
-    from crisperwhisper_b200 import adjust_pauses_for_hf_pipeline_output
+
+    def e2e_step():
+        if world == 1:
+            res = pipe(waves_host, generate_kwargs=gk)
+            return [adjust_pauses_for_hf_pipeline_output(r) for r in res], pipe.last_stats
+        # cfg 4: every rank runs stages 1-3 on its round-robin share, the per-chunk records are all-gathered, rank 0 turns
+        # all of them into words (tokenizer-level _decode_asr restatement) and adjusts the pauses
+        mo = pipe.forward(waves_host, generate_kwargs=gk)
+        st = dict(pipe.last_stats)
+        local = [(o[0]["tokens"][0], o[0]["token_timestamps"][0]) for o in mo]
+        full = D.gather_results(local, NC * world, dev)
+        st["d2h_bytes"] = st.get("d2h_bytes", 0) + sum(a.nbytes + b.nbytes for a, b in full)
+        res = None
+        if rank == 0:
+            res = []
+            for tk, ts in full:
+                r = pipe.postprocess([{"tokens": tk[None, :], "token_timestamps": ts[None, :], "is_last": True, "stride": (480000, 0, 0)}])
+                res.append(adjust_pauses_for_hf_pipeline_output(r))
+        return res, st
+
     for _ in range(2):
-        res = pipe(waves_host, generate_kwargs=gk)
+        e2e_step()
     barrier()
     e2e_times = []
     for _ in range(max(2, min(args.steps, 5))):
+        barrier()
         tt = time.perf_counter()
-        res = pipe(waves_host, generate_kwargs=gk)
-        res = [adjust_pauses_for_hf_pipeline_output(r) for r in res]
+        res, st = e2e_step()
         torch.cuda.synchronize()
-        e2e_times.append(time.perf_counter() - tt)
-    e2e_s = torch.tensor([float(np.median(e2e_times))], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_val = audio_s / float(e2e_s.item())
-    st = pipe.last_stats
-    # gather of transcripts (cfg 4's end collective): fixed-size records, timed separately
-    local = [(np.zeros(T, np.int64), np.zeros(T, np.float32)) for _ in range(B)]  # fixed-size records, as in cfg 4
-    tg = time.perf_counter()
-    D.gather_results(local, B * world, dev)
-    torch.cuda.synchronize()
-    gather_ms = (time.perf_counter() - tg) * 1000.0
+        e2e_times.append(max_over_ranks(time.perf_counter() - tt))
+    e2e_s = float(np.median(e2e_times))
+    e2e_val = audio_s / e2e_s
+
+    # ---- cfg 5 on every rank: 1024 utterances x 20 heads x 448 x 1500, sharded N ways ------------------------------------------
+    stages = {}
+    if not args.no_extras:
+        n_utt = 1024 // world
+        sub = 128
+        al_buf = torch.empty(sub, 20, 448, 1500, dtype=torch.float32, device=dev)
+        Tl = torch.full((sub,), 448, dtype=torch.int32, device=dev)
+        Fl = torch.full((sub,), 1500, dtype=torch.int32, device=dev)
+        tt = torch.arange(448, device=dev, dtype=torch.float32)[None, None, :, None]
+        ff = torch.arange(1500, device=dev, dtype=torch.float32)[None, None, None, :]
+        peak_term = 6.0 * torch.exp(-(((ff - tt * 1500.0 / 448.0) / 20.0) ** 2))
+        gen = torch.Generator(device=dev)
+        tot_ms = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(0, n_utt, sub):
+            gen.manual_seed(1000 * rank + i)
+            for j in range(0, sub, 8):   # softmax_F(3 z + 6 exp(-((f - t F/T)/20)^2)), generated on the device (SURVEY 8d cfg 5)
+                z = torch.randn(8, 20, 448, 1500, generator=gen, device=dev)
+                al_buf[j:j + 8] = torch.softmax(3.0 * z + peak_term, -1)
+            if i == 0:
+                eng.align(al_buf, Tl, Fl, 7)   # warm-up
+            eng.sync()
+            e0.record(eng.stream)
+            eng.align(al_buf, Tl, Fl, 7)
+            e1.record(eng.stream)
+            eng.sync()
+            tot_ms += e0.elapsed_time(e1)
+        del al_buf, z
+        dtw_ms = max_over_ranks(tot_ms)
+        dtw_bytes = 1024 * (20 * 448 * 1500 * 4 + 448 * 4)
+        stages["dtw_cfg5"] = {"workload": f"cfg5: 1024 utterances x 20 heads x 448 x 1500 f32, {n_utt} per GPU on {world} GPU(s), in resident sub-batches of {sub}",
+                              "ms_max_over_ranks": round(dtw_ms, 3), "achieved_GBs_whole_job": round(dtw_bytes / (dtw_ms * 1e-3) / 1e9, 1),
+                              "achieved_GBs_per_gpu": round(dtw_bytes / world / (dtw_ms * 1e-3) / 1e9, 1), "peak_GBs_per_gpu": peaks["hbm"],
+                              "frac": round(dtw_bytes / world / (dtw_ms * 1e-3) / 1e9 / peaks["hbm"], 4), "bound": "hbm",
+                              "kernels": "align_reduce_kernel + dtw_kernel"}
 
     if rank != 0:
         if world > 1:
@@ -332,93 +397,115 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events ----------------------------------------------
-    # At B <= 8 one decode step is ONE launch of decode_mega_kernel (persistent cooperative kernel); the T + n_prompt - 1
-    # launches of a decode call are timed back to back with CUDA events on the engine stream.
-    peaks = measured_peaks()
-    _, tm, _ = eng.logmel(wave_dev, filt, None, want_f32=False, want_tm=True)
-    xkv, _ = eng.encode(tm)
-    eng.decode(xkv, prompt, T, flags=flags)
-    eng.sync()
-    n_launch = T + n_prompt - 1
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dec_ms = []
-    for _ in range(3):
-        d0.record(eng.stream)
+    # ---- roofline of the dominant kernel (rank 0), measured live with CUDA events --------------------------------------------------
+    # decode_stream_kernel: one cooperative launch = up to 16 decode steps of the whole decode batch; a decode call of T new
+    # tokens is ceil((T + n_prompt - 1) / 16) launches, timed back to back on the engine stream.
+    def decode_roofline(bd):
+        wv = wave_dev[:bd] if wave_dev.shape[0] >= bd else torch.from_numpy(np.stack([synth_wave(900 + i) for i in range(bd)])).to(dev)
+        _, tm, _ = eng.logmel(wv, filt, None, want_f32=False, want_tm=True)
+        xkv, _ = eng.encode(tm)
+        prompt = torch.tensor([[50258, 50259, 50360]] * bd, dtype=torch.int32, device=dev)
         eng.decode(xkv, prompt, T, flags=flags)
-        d1.record(eng.stream)
         eng.sync()
-        dec_ms.append(d0.elapsed_time(d1))
-    per_launch_ms = float(np.median(dec_ms)) / n_launch
-    d, H, F, Ld, ffn, Vp = cfg["d_model"], cfg["n_heads"], 1500, cfg["dec_layers"], cfg["ffn_dim"], cfg["vocab_padded"]
-    w_bytes = Ld * (3 * d * d + 3 * d * d + 2 * d * ffn) * 2 + Vp * d * 2       # qkv, o, q_c, o_c, fc1, fc2 + tied proj_out
-    xkv_bytes = Ld * B * H * F * 2 * 64 * 2                                      # cross K and V of every sample
-    self_bytes = Ld * B * 2 * d * 2 * (n_prompt + T) // 2                        # self KV cache, mean length
-    align_bytes = B * 20 * F * 4                                                 # alignment-head rows written
-    step_bytes = w_bytes + xkv_bytes + self_bytes + align_bytes
-    achieved = step_bytes / (per_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "decode_mega_kernel (one launch = one decode step of the whole batch)",
-                "achieved": round(achieved, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(achieved / peaks["hbm"], 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch, ncu --set full
-                # (profiles/r01_ncu_summary.md: 3.574 GB read + 11 MB written)
-                "traffic": 3619000000, "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
-                "algorithmic_bytes_per_launch": int(step_bytes), "avg_launch_ms": round(per_launch_ms, 4),
-                "launches_timed": n_launch * 3,
-                "bytes_breakdown_GB": {"decoder_weights": round(w_bytes / 1e9, 3), "cross_kv": round(xkv_bytes / 1e9, 3),
-                                       "self_kv_mean": round(self_bytes / 1e9, 3), "alignment_rows": round(align_bytes / 1e9, 4)},
-                "share_of_step": round(float(np.median(dec_ms)) / ms_per_step, 3)}
-    # per-operator view (one kernel per operator, direct launches, events between kernels)
-    Tp = min(T, 48)
-    eng.decode(xkv, prompt, Tp, flags=flags | L.CW_DEC_PROFILE)
-    eng.sync()
-    pms, pn = eng.decode_profile()
-    tot = sum(pms) or 1.0
-    roofline["per_operator_time_shares"] = {c: round(m / tot, 4) for c, m in zip(["gemv(weights)", "self_attn", "cross_attn", "other"], pms)}
+        n_steps = T + n_prompt - 1
+        n_launch = (n_steps + 15) // 16
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dec_ms = []
+        for _ in range(3):
+            d0.record(eng.stream)
+            eng.decode(xkv, prompt, T, flags=flags)
+            d1.record(eng.stream)
+            eng.sync()
+            dec_ms.append(d0.elapsed_time(d1))
+        call_ms = float(np.median(dec_ms))
+        d, H, F, Ld, ffn, Vp = cfg["d_model"], cfg["n_heads"], 1500, cfg["dec_layers"], cfg["ffn_dim"], cfg["vocab_padded"]
+        w_bytes = Ld * (3 * d * d + 3 * d * d + 2 * d * ffn) * 2 + Vp * d * 2       # qkv, o, q_c, o_c, fc1, fc2 + tied proj_out
+        xkv_bytes = Ld * bd * H * F * 2 * 64 * 2                                     # cross K and V of every sample
+        self_bytes = Ld * bd * 2 * d * 2 * (n_prompt + T) // 2                       # self KV cache, mean length
+        align_bytes = bd * 20 * F * 4                                                # alignment-head rows written
+        step_bytes = w_bytes + xkv_bytes + self_bytes + align_bytes
+        achieved = step_bytes * n_steps / (call_ms * 1e-3) / 1e9
+        return dict(batch=bd, ms_per_decode_step=round(call_ms / n_steps, 4), avg_launch_ms=round(call_ms / n_launch, 3),
+                    launches_timed=3 * n_launch, steps_per_launch=16, algorithmic_bytes_per_step=int(step_bytes),
+                    achieved=round(achieved, 1), frac=round(achieved / peaks["hbm"], 4), call_ms=call_ms,
+                    bytes_breakdown_GB={"decoder_weights": round(w_bytes / 1e9, 3), "cross_kv": round(xkv_bytes / 1e9, 3),
+                                        "self_kv_mean": round(self_bytes / 1e9, 3), "alignment_rows": round(align_bytes / 1e9, 4)})
 
-    extras = {}
+    r = decode_roofline(Bd)
+    prof, prof_path = traffic_from_profile()
+    traffic = None
+    if prof and prof.get("dram_bytes_per_launch") and prof.get("steps_in_launch"):
+        traffic = int(prof["dram_bytes_per_launch"] / prof["steps_in_launch"] * 16)
+    roofline = {"bound": "hbm", "kernel": "decode_stream_kernel (one cooperative launch = 16 decode steps of the whole decode batch)",
+                "achieved": r["achieved"], "peak": peaks["hbm"], "unit": "GB/s", "frac": r["frac"],
+                "traffic": traffic,
+                "traffic_source": (f"{prof_path}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                   f"({prof.get('steps_in_launch')} steps, commit {prof.get('commit')}), scaled to 16 steps") if prof else None,
+                "peak_source": peaks["src"] + " (of measured, sustained-copy figure)",
+                "algorithmic_bytes_per_launch": int(r["algorithmic_bytes_per_step"] * 16), "avg_launch_ms": r["avg_launch_ms"],
+                "ms_per_decode_step": r["ms_per_decode_step"], "launches_timed": r["launches_timed"],
+                "bytes_breakdown_GB_per_step": r["bytes_breakdown_GB"], "decode_batch": Bd,
+                "share_of_step": round(r["call_ms"] * ((NC + Bd - 1) // Bd) / ms_per_step, 3)}
+
+    alt = None
     if not args.no_extras:
-        # encoder-GEMM tensor roofline (fc1 shape of the encoder at this batch) and the stage-3 HBM roofline (cfg-5 shape)
-        M = B * 1500
+        # ---- other decode batches / lengths, whole-encoder tensor roofline, cfg 3, cfg 4 share ---------------------------------------
+        other = 16 if Bd == 8 else 8
+        ro = decode_roofline(other)
+        stages["decode_other_batch"] = {k: ro[k] for k in ("batch", "ms_per_decode_step", "achieved", "frac")}
+        if T != 128:
+            w8 = wave_dev[:min(8, NC)]
+            t128 = time_device(lambda: run_chunks(w8, min(8, NC), 128, gather=False), 2, 1)
+            alt = {"new_tokens": 128, "ms_per_step": round(t128, 2), "value": round(30.0 * w8.shape[0] / (t128 / 1000.0), 1),
+                   "note": "8 chunks with 128 new tokens per chunk (typical for 30 s of speech), one GPU; not the headline"}
+        # whole encoder + cross-K/V (conv as GEMM, 32 layers, attention, final LN, K/V projection): 2588.4 GFLOP per chunk
+        _, tm8, _ = eng.logmel(wave_dev[:min(8, NC)], filt, None, want_f32=False, want_tm=True)
+        nb8 = tm8.shape[0]
+        enc_ms = time_device(lambda: eng.encode(tm8), 5, 2)
+        enc_tf = nb8 * 2588.4e9 / (enc_ms * 1e-3) / 1e12
+        stages["encoder_whole"] = {"batch": nb8, "ms": round(enc_ms, 3), "achieved_TFLOPs": round(enc_tf, 1), "GFLOP_per_chunk": 2588.4,
+                                   "peak_TFLOPs_sustained": peaks["tf_sust"], "frac_of_sustained": round(enc_tf / peaks["tf_sust"], 4),
+                                   "peak_TFLOPs_burst": peaks["tf_burst"], "frac_of_burst": round(enc_tf / peaks["tf_burst"], 4), "bound": "tensor"}
+        M = nb8 * 1500
         A = (torch.randn(M, 1280, device=dev) * 0.5).to(torch.bfloat16)
         W = (torch.randn(5120, 1280, device=dev) * 0.5).to(torch.bfloat16)
-        for _ in range(3):
-            eng.gemm(A, W)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eng.sync()
-        e0.record(eng.stream)
-        for _ in range(20):
-            eng.gemm(A, W)
-        e1.record(eng.stream)
-        eng.sync()
-        gms = e0.elapsed_time(e1) / 20
+        gms = time_device(lambda: eng.gemm(A, W), 20, 3)
         tf = 2.0 * M * 5120 * 1280 / (gms * 1e-3) / 1e12
-        extras["encoder_gemm"] = {"shape": [M, 5120, 1280], "ms": round(gms, 4), "achieved_TFLOPs": round(tf, 1),
+        stages["encoder_gemm"] = {"shape": [M, 5120, 1280], "ms": round(gms, 4), "achieved_TFLOPs": round(tf, 1),
                                   "peak_TFLOPs": peaks["tf_burst"], "frac": round(tf / peaks["tf_burst"], 4), "bound": "tensor"}
-        N5 = 128
-        al = torch.softmax(torch.randn(N5, 20, 448, 1500, device=dev) * 3, -1)
-        Tl = torch.full((N5,), 448, dtype=torch.int32, device=dev)
-        Fl = torch.full((N5,), 1500, dtype=torch.int32, device=dev)
-        for _ in range(2):
-            eng.align(al, Tl, Fl, 7)
-        eng.sync()
-        e0.record(eng.stream)
-        for _ in range(5):
-            eng.align(al, Tl, Fl, 7)
-        e1.record(eng.stream)
-        eng.sync()
-        ams = e0.elapsed_time(e1) / 5
-        gbs = N5 * (20 * 448 * 1500 * 4 + 448 * 4) / (ams * 1e-3) / 1e9
-        extras["align_dtw"] = {"shape": [N5, 20, 448, 1500], "ms": round(ams, 3), "achieved_GBs": round(gbs, 1),
-                               "peak_GBs": peaks["hbm"], "frac": round(gbs / peaks["hbm"], 4), "bound": "hbm",
-                               "note": "align_reduce_kernel + dtw_kernel, cfg-5 shape on a 128-utterance subset (6.9 GB)"}
-        del al, A, W
+        del A, W
+        if world == 1:
+            # cfg 3: 10-minute clip -> 30 chunks (29 x 30 s + 20 s, 5 s strides), batch 16, through the public pipeline incl. the
+            # stride merge and the pause adjustment; host waveform in, dict out
+            rng = np.random.default_rng(77)
+            long_wave = (rng.standard_normal(9600000) * 0.1).astype(np.float32)
+            pipe16 = pipeline("automatic-speech-recognition", model=eng, tokenizer=tok, feature_extractor=None, chunk_length_s=30,
+                              batch_size=16, return_timestamps="word")
+            adjust_pauses_for_hf_pipeline_output(pipe16(long_wave, generate_kwargs=gk))
+            lt = []
+            for _ in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                o3 = adjust_pauses_for_hf_pipeline_output(pipe16(long_wave, generate_kwargs=gk))
+                torch.cuda.synchronize()
+                lt.append(time.perf_counter() - t0)
+            stages["longform_cfg3"] = {"workload": f"cfg3: 10 min clip -> {pipe16.last_stats['chunks']} chunks (30 s / 5 s stride), batch 16, {T} new tokens per chunk, "
+                                                   "pipeline(...) + stride merge + adjust_pauses, host in / dict out",
+                                       "seconds": round(float(np.median(lt)), 3), "value": round(600.0 / float(np.median(lt)), 1), "unit": UNIT,
+                                       "words": len(o3["chunks"])}
+            # cfg 4's per-GPU share on this one GPU (32 chunks, decode batch 16) so that the N-GPU lines can be compared at equal work
+            w32 = torch.from_numpy(np.stack([synth_wave(500 + i) for i in range(32)])).to(dev)
+            t32 = time_device(lambda: run_chunks(w32, 16, T, gather=False), 2, 1)
+            stages["cfg4_share_one_gpu"] = {"workload": f"32 chunks x 30 s per GPU (cfg 4: 256 over 8), decode batch 16, {T} new tokens, device-timed",
+                                            "ms_per_step": round(t32, 1), "value": round(960.0 / (t32 / 1000.0), 1), "unit": UNIT}
+            del w32
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--new-tokens",
                                   str(T), "--ref-tokens", str(args.ref_tokens), "--ref-threads", str(args.ref_threads)],
-                                 capture_output=True, text=True, timeout=600,
+                                 capture_output=True, text=True, timeout=900,
                                  env={**os.environ, "RANK": "0", "WORLD_SIZE": "1", "CUDA_VISIBLE_DEVICES": ""})
             ref_line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
             cpu_baseline = ref_line["cpu_baseline"]
@@ -426,19 +513,27 @@ def main():
         except Exception as e:  # pragma: no cover
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
+    wl = (f"cfg2: batch={NC} x 30 s synthetic 16 kHz chunks on one GPU" if world == 1 else
+          f"cfg4 share: {NC} x 30 s chunks per GPU ({NC * world} chunks round-robin over {world} GPUs), decode batches of {Bd}, transcript "
+          "all_gather inside the timed region (e2e: + word decoding of all chunks on rank 0)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"cfg2: batch={B} x 30 s synthetic 16 kHz chunks per GPU, CrisperWhisper large-v3 shape (random init), "
-                               f"greedy decode {T} new tokens (EOS suppressed) + 20-head median-7 DTW alignment",
-                   "new_tokens": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (chunks round-robin)",
-                   "l2": "working set per step (3.1 GB weights + 2 GB cross-K/V) >> 126 MB L2; no explicit flush",
-                   "weights_broadcast_ms": round(bcast_ms, 2), "transcript_gather_ms": round(gather_ms, 2)},
+        "config": {"workload": wl + f", CrisperWhisper large-v3 shape (random init), greedy decode {T} new tokens (EOS suppressed) + "
+                                    "20-head median-7 DTW alignment",
+                   "new_tokens": T, "chunks_per_gpu": NC, "decode_batch": Bd, "global_chunks": NC * world,
+                   "parallelism": f"dp{world} (chunk i -> rank i mod {world})",
+                   "l2": "working set per step (3.1 GB weights + 1.7 GB fragment-major copies + 2-4 GB cross-K/V) >> 126 MB L2; no explicit flush",
+                   "weights_broadcast_ms": round(bcast_ms, 2),
+                   "note": "one GPU measures cfg 2 (8 chunks); several GPUs measure cfg 4's share (32 chunks per GPU); "
+                           "stages.cfg4_share_one_gpu gives the one-GPU number at the multi-GPU per-GPU work"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(st.get("h2d_bytes", 0)),
-                "d2h_bytes_per_step": int(st.get("d2h_bytes", 0)), "api": "crisperwhisper_b200.pipeline(...)(list of np.ndarray) + adjust_pauses",
-                "ms_per_step": round(float(e2e_s.item()) * 1000.0, 2)},
-        "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "stages": extras,
+                "d2h_bytes_per_step": int(st.get("d2h_bytes", 0)),
+                "api": "crisperwhisper_b200.pipeline(...)(list of np.ndarray) + adjust_pauses" if world == 1 else
+                       "pipeline.forward(host chunks) per rank + distributed.gather_results + pipeline.postprocess + adjust_pauses on rank 0",
+                "ms_per_step": round(e2e_s * 1000.0, 2)},
+        "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "stages": stages,
         "alt_decode_length": alt,
     }
     print(json.dumps(line), flush=True)

@@ -104,6 +104,23 @@ class AutomaticSpeechRecognitionPipeline:
         results = [self._postprocess(mo, rt) for mo in per_input]
         return results if is_list else results[0]
 
+    def forward(self, inputs, return_timestamps=None, generate_kwargs: Optional[Dict] = None, batch_size=None, chunk_length_s=None):
+        """Stages 1-3 only (HF preprocess + _forward): per input, the list of per-chunk model outputs
+        {"tokens", "token_timestamps", "stride", "is_last"} that `postprocess` turns into {"text","chunks"}.  A multi-GPU job
+        gathers these small records (distributed.gather_results) and runs `postprocess` on one rank (BASELINE cfg 4)."""
+        items = list(inputs) if isinstance(inputs, (list, tuple)) else [inputs]
+        rt = return_timestamps if return_timestamps is not None else self.return_timestamps
+        gk = dict(self.generate_kwargs)
+        gk.update(generate_kwargs or {})
+        bs = self.batch_size if batch_size is None else max(1, int(batch_size))
+        cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
+        waves = [A.normalize_input(x, self._resample) for x in items]
+        return self._run(waves, cl, bs, gk, rt)
+
+    def postprocess(self, model_outputs: List[Dict], return_timestamps=None):
+        rt = return_timestamps if return_timestamps is not None else self.return_timestamps
+        return self._postprocess(model_outputs, rt)
+
     def _resample(self, x: np.ndarray, sr_in: int) -> np.ndarray:
         """Host waveform at sr_in -> 16 kHz through cw_resample (HF preprocess :394-408 calls torchaudio here)."""
         dev = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.engine.device)

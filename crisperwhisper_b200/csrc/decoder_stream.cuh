@@ -1037,18 +1037,17 @@ __device__ __noinline__ uint32_t s_ph_cross(const SPhase* D, int pos, uint32_t s
     float* part = c_sp.xpart + ((size_t)task * c_sp.part_stride + it.seg) * 66;
     if (gtid < 64) part[2 + gtid] = base[32 + gtid];
     if (gtid == 0) { part[0] = ml.x; part[1] = ml.y; }
-    __threadfence();
-    named_bar(2 + gi, 128);
+    named_bar(2 + gi, 128);   // the group's partial (and raw scores) are written; one acq_rel atomic publishes them
     const int ns = it.ns;
     if (gtid == 0) {
-      const unsigned int old = atomicAdd(c_sp.xcount + task, 1u);
+      unsigned int old;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(c_sp.xcount + task) : "memory");
       s_flag[gi] = (old == (unsigned int)(ns - 1)) ? 1 : 0;
       if (old == (unsigned int)(ns - 1)) c_sp.xcount[task] = 0;
     }
     named_bar(2 + gi, 128);
     S_SUB(2);
     if (s_flag[gi]) {
-      __threadfence();
       const float* pt = c_sp.xpart + (size_t)task * c_sp.part_stride * 66;
       float M = -INFINITY;
       for (int k = 0; k < ns; ++k) M = fmaxf(M, ld_cg(pt + k * 66));
@@ -1150,12 +1149,32 @@ __device__ __noinline__ void s_sample_embed(int pos, bool embed) {
   }
   if (!embed) return;
   cons_bar();
-  const float* ptab = c_sp.dec_pos + (size_t)pos * d;
-  for (int i = tid; i < B * d; i += kSConsThreads) {
-    const int b = i / d, k = i - b * d;
-    const int tok = c_sp.seq[(size_t)b * c_sp.n_ctx + pos];
-    const float xv = __bfloat162float(c_sp.tok_emb[(size_t)tok * d + k]) + ptab[k];
-    for (int r = 0; r < c_sp.R; ++r) c_sp.x[(size_t)r * B * d + i] = xv;
+  // x = tok_emb[token] + pos: 512 / B threads per sample, the token id read once, every thread's embedding loads (HBM
+  // misses: the row was last touched a step ago) all in flight at once
+  const int tps = kSConsThreads / ((B <= 8) ? 8 : 16);          // threads per sample
+  const int b = tid / tps, k0 = tid - b * tps;
+  if (b < B) {
+    const float* ptab = c_sp.dec_pos + (size_t)pos * d;
+    const int tok = __ldcg(c_sp.seq + (size_t)b * c_sp.n_ctx + pos);
+    const bf16* erow = c_sp.tok_emb + (size_t)tok * d;
+    constexpr int U = 8;
+    for (int kb = k0; kb < d; kb += U * tps) {
+      float ev[U], pv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * tps;
+        ev[u] = (k < d) ? __bfloat162float(erow[k]) : 0.f;
+        pv[u] = (k < d) ? __ldg(ptab + k) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * tps;
+        if (k < d) {
+          const float xv = ev[u] + pv[u];
+          for (int r = 0; r < c_sp.R; ++r) c_sp.x[((size_t)r * B + b) * d + k] = xv;
+        }
+      }
+    }
   }
 }
 

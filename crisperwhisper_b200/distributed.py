@@ -37,27 +37,37 @@ def broadcast_weights(packed: Optional[Wt.PackedWeights], config: Dict, device, 
     return pw
 
 
-def pack_result(tokens: np.ndarray, token_ts: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-    """-> (int32 [N_TOK + 1] = tokens padded with -1 then the length, float32 [N_TOK])."""
-    n = min(len(tokens), N_TOK)
-    t = np.full(N_TOK + 1, -1, np.int32)
+def pack_result(tokens: np.ndarray, token_ts: np.ndarray, n_tok: int = N_TOK) -> Tuple[np.ndarray, np.ndarray]:
+    """-> (int32 [n_tok + 1] = tokens padded with -1 then the length, float32 [n_tok]).  A chunk that does not fit the
+    record is an error (a chunk that needed several seek passes can exceed 448 tokens: gather_results sizes the record from
+    the all-reduced maximum, so nothing is ever truncated silently)."""
+    n = len(tokens)
+    if n > n_tok:
+        raise ValueError(f"pack_result: {n} tokens do not fit a record of {n_tok}")
+    t = np.full(n_tok + 1, -1, np.int32)
     t[:n] = tokens[:n]
-    t[N_TOK] = n
-    ts = np.zeros(N_TOK, np.float32)
-    ts[:n] = token_ts[:n]
+    t[n_tok] = n
+    ts = np.zeros(n_tok, np.float32)
+    m = min(n, len(token_ts))
+    ts[:m] = token_ts[:m]
     return t, ts
 
 
 def gather_results(local: List[Tuple[np.ndarray, np.ndarray]], n_items: int, device) -> Optional[List[Tuple[np.ndarray, np.ndarray]]]:
     """local: results of this rank's round-robin shard, in shard order.  Returns the full list in item order on
-    every rank (all_gather of fixed-size records; ~3.6 KB per chunk)."""
+    every rank (all_gather of fixed-size records; ~3.6 KB per chunk; the record length is the all-reduced maximum
+    token count, at least 448)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
     per_rank = (n_items + world - 1) // world
-    ti = torch.full((per_rank, N_TOK + 1), -1, dtype=torch.int32)
-    tf = torch.zeros((per_rank, N_TOK), dtype=torch.float32)
+    n_tok = max([N_TOK] + [len(tok) for tok, _ in local])
+    if world > 1:
+        nt = torch.tensor([n_tok], dtype=torch.int64, device=device)
+        dist.all_reduce(nt, op=dist.ReduceOp.MAX)
+        n_tok = int(nt.item())
+    ti = torch.full((per_rank, n_tok + 1), -1, dtype=torch.int32)
+    tf = torch.zeros((per_rank, n_tok), dtype=torch.float32)
     for k, (tok, ts) in enumerate(local):
-        a, b = pack_result(tok, ts)
+        a, b = pack_result(tok, ts, n_tok)
         ti[k] = torch.from_numpy(a)
         tf[k] = torch.from_numpy(b)
     ti, tf = ti.to(device), tf.to(device)
@@ -72,6 +82,6 @@ def gather_results(local: List[Tuple[np.ndarray, np.ndarray]], n_items: int, dev
     for r in range(world):
         ai, af = gi[r].cpu().numpy(), gf[r].cpu().numpy()
         for k, item in enumerate(shard_round_robin(n_items, r, world)):
-            n = int(ai[k, N_TOK])
+            n = int(ai[k, n_tok])
             out[item] = (ai[k, :n].astype(np.int64), af[k, :n].copy())
     return out
