@@ -284,17 +284,18 @@ def main():
                 dist.all_gather(gj, jmp)
         return outs
 
-    def time_device(fn, steps, warm):
+    def time_local(fn, steps, warm):
+        """CUDA-event timing on this rank only (no collective: safe in the rank-0-only part of the script)."""
         for _ in range(warm):
             fn()
-        barrier()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(eng.stream)
         for _ in range(steps):
             fn()
         e1.record(eng.stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1) / steps)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
 
     # ---- headline: device-timed step -----------------------------------------------------------------------------------
     waves_host = [synth_wave(i * world + rank) for i in range(NC)]            # chunk i -> rank i mod W (cfg 4 layout)
@@ -391,10 +392,11 @@ def main():
                               "frac": round(dtw_bytes / world / (dtw_ms * 1e-3) / 1e9 / peaks["hbm"], 4), "bound": "hbm",
                               "kernels": "align_reduce_kernel + dtw_kernel"}
 
+    # last collective of the run: everything below is rank-0-only and must not touch the process group
+    if world > 1:
+        dist.barrier()
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (rank 0), measured live with CUDA events --------------------------------------------------
@@ -455,13 +457,13 @@ def main():
         stages["decode_other_batch"] = {k: ro[k] for k in ("batch", "ms_per_decode_step", "achieved", "frac")}
         if T != 128:
             w8 = wave_dev[:min(8, NC)]
-            t128 = time_device(lambda: run_chunks(w8, min(8, NC), 128, gather=False), 2, 1)
+            t128 = time_local(lambda: run_chunks(w8, min(8, NC), 128, gather=False), 2, 1)
             alt = {"new_tokens": 128, "ms_per_step": round(t128, 2), "value": round(30.0 * w8.shape[0] / (t128 / 1000.0), 1),
                    "note": "8 chunks with 128 new tokens per chunk (typical for 30 s of speech), one GPU; not the headline"}
         # whole encoder + cross-K/V (conv as GEMM, 32 layers, attention, final LN, K/V projection): 2588.4 GFLOP per chunk
         _, tm8, _ = eng.logmel(wave_dev[:min(8, NC)], filt, None, want_f32=False, want_tm=True)
         nb8 = tm8.shape[0]
-        enc_ms = time_device(lambda: eng.encode(tm8), 5, 2)
+        enc_ms = time_local(lambda: eng.encode(tm8), 5, 2)
         enc_tf = nb8 * 2588.4e9 / (enc_ms * 1e-3) / 1e12
         stages["encoder_whole"] = {"batch": nb8, "ms": round(enc_ms, 3), "achieved_TFLOPs": round(enc_tf, 1), "GFLOP_per_chunk": 2588.4,
                                    "peak_TFLOPs_sustained": peaks["tf_sust"], "frac_of_sustained": round(enc_tf / peaks["tf_sust"], 4),
@@ -469,7 +471,7 @@ def main():
         M = nb8 * 1500
         A = (torch.randn(M, 1280, device=dev) * 0.5).to(torch.bfloat16)
         W = (torch.randn(5120, 1280, device=dev) * 0.5).to(torch.bfloat16)
-        gms = time_device(lambda: eng.gemm(A, W), 20, 3)
+        gms = time_local(lambda: eng.gemm(A, W), 20, 3)
         tf = 2.0 * M * 5120 * 1280 / (gms * 1e-3) / 1e12
         stages["encoder_gemm"] = {"shape": [M, 5120, 1280], "ms": round(gms, 4), "achieved_TFLOPs": round(tf, 1),
                                   "peak_TFLOPs": peaks["tf_burst"], "frac": round(tf / peaks["tf_burst"], 4), "bound": "tensor"}
@@ -495,13 +497,13 @@ def main():
                                        "words": len(o3["chunks"])}
             # cfg 4's per-GPU share on this one GPU (32 chunks, decode batch 16) so that the N-GPU lines can be compared at equal work
             w32 = torch.from_numpy(np.stack([synth_wave(500 + i) for i in range(32)])).to(dev)
-            t32 = time_device(lambda: run_chunks(w32, 16, T, gather=False), 2, 1)
+            t32 = time_local(lambda: run_chunks(w32, 16, T, gather=False), 2, 1)
             stages["cfg4_share_one_gpu"] = {"workload": f"32 chunks x 30 s per GPU (cfg 4: 256 over 8), decode batch 16, {T} new tokens, device-timed",
                                             "ms_per_step": round(t32, 1), "value": round(960.0 / (t32 / 1000.0), 1), "unit": UNIT}
             del w32
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is timed on rank 0 at N = 1 only
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--new-tokens",
                                   str(T), "--ref-tokens", str(args.ref_tokens), "--ref-threads", str(args.ref_threads)],
@@ -538,7 +540,6 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
 
 
