@@ -969,7 +969,7 @@ static int plan_cross_items(int tasks, int F, int cr, int n_cta, std::vector<XIt
           memset(&it, 0, sizeof(it));
           it.task = sg.task; it.f0 = (short)(ch * cr); it.nf = (short)((F - ch * cr < cr) ? F - ch * cr : cr);
           it.group = (signed char)gi; it.seg = (short)sg.seg; it.ns = (short)(*splits)[sg.task];
-          it.flags = (signed char)((k == 0 ? 1 : 0) | (k == sg.nc - 1 ? 2 : 0));
+          it.flags = (signed char)((k == 0 ? 1 : 0) | (k == sg.nc - 1 ? 2 : 0) | (&sg == &slot[(size_t)c * 4 + gi][0] ? 4 : 0));
           grp[gi].push_back(it);
         }
     }

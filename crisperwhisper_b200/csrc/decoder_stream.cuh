@@ -182,7 +182,7 @@ __device__ __forceinline__ void grid_arrive_and_wait(unsigned int* bar, unsigned
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int spins = 0;
     unsigned long long t0 = 0;
-    while (true) {
+    while (true) {   // (relaxed polls + one fence.acq_rel at the end were measured slower: 1.45 vs 1.05 us per barrier)
       unsigned int v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if ((int)(v - target) >= 0) break;
@@ -651,7 +651,8 @@ __device__ __noinline__ uint32_t s_ph_gemv(const SPhase* D, int pos, uint32_t se
     S_SUB(5);
     if (tb + TB < cnt) cons_bar();  // red is rewritten by the next batch
   }
-  if (!LOGITS && epi == EPI_QKV) asm volatile("fence.proxy.async;" ::: "memory");  // cache rows are read by later steps' bulk copies
+  // K/V cache rows written here are read by later steps' bulk copies (async proxy): the writers fence, cheaply (global only)
+  if (!LOGITS && epi == EPI_QKV && em < B) asm volatile("fence.proxy.async.global;" ::: "memory");
   if (LOGITS) {
     // combine the 32 threads (4 tiles x 8 rows) that share a sample, then one record per (CTA, sample)
     cons_bar();
@@ -911,11 +912,12 @@ __device__ __forceinline__ void attn_chunk(AState& S, const float* qv, uint32_t 
   }
 }
 
-// merge the 16 row-subgroups of a group: on return (every thread) M, L and so[0..63] = sum_j 2^(s_j - M) v_j
-__device__ __forceinline__ float2 attn_group_merge(const AState& S, float* base, int gtid, int bar_id) {
+// merge the 16 row-subgroups of a group: returns (M, L) to every thread and, to threads gtid < 64, out = sum_j 2^(s_j - M) v_j
+// of dimension gtid in `outv`. `first` = the scratch has not been used since the last grid barrier (no protecting barrier needed).
+__device__ __forceinline__ float2 attn_group_merge(const AState& S, float* base, int gtid, int bar_id, bool first, float& outv) {
   const int sub = gtid & 7, r = gtid >> 3;
   float* smx = base; float* sl = base + 16; float* so = base + 32;
-  named_bar(bar_id, 128);   // the scratch may still be read by the previous segment's tail
+  if (!first) named_bar(bar_id, 128);   // the scratch may still be read by the previous segment's tail
   if (sub == 0) { smx[r] = S.m; sl[r] = S.l; }
 #pragma unroll
   for (int e = 0; e < 8; ++e) so[r * 64 + sub * 8 + e] = S.acc[e];
@@ -931,9 +933,7 @@ __device__ __forceinline__ float2 attn_group_merge(const AState& S, float* base,
 #pragma unroll
     for (int i = 0; i < 16; ++i) v += so[i * 64 + gtid] * ex2_approx(smx[i] - M);
   }
-  named_bar(bar_id, 128);
-  if (gtid < 64) so[gtid] = v;
-  named_bar(bar_id, 128);
+  outv = v;
   return make_float2(M, L);
 }
 
@@ -976,19 +976,21 @@ __device__ __noinline__ uint32_t s_ph_self(const SPhase* D, int pos, uint32_t se
       }
       S_SUB(1);
       if ((warp & 3) == 0) {  // the row of this step (written by the qkv phase) straight from L2, by the first 8 threads
-        const bool live = gtid < 8;
-        uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
-        if (live) {
+        // (requesting it before the chunk loop was measured slower: the loop then waits on the same scoreboard)
+        const bool nr_live = gtid < 8;
+        uint4 nk = make_uint4(0, 0, 0, 0), nvv = make_uint4(0, 0, 0, 0);
+        if (nr_live) {
           const size_t off = ((size_t)task * c_sp.n_ctx + pos) * 64 + sub * 8;
-          ku = ld_cg16(reinterpret_cast<const uint4*>(c_sp.kc + (size_t)D->l * cache_l + off));
-          vu = ld_cg16(reinterpret_cast<const uint4*>(c_sp.vc + (size_t)D->l * cache_l + off));
+          nk = ld_cg16(reinterpret_cast<const uint4*>(c_sp.kc + (size_t)D->l * cache_l + off));
+          nvv = ld_cg16(reinterpret_cast<const uint4*>(c_sp.vc + (size_t)D->l * cache_l + off));
         }
-        attn_row(S, qv, ku, vu, live, nullptr);
+        attn_row(S, qv, nk, nvv, nr_live, nullptr);
       }
-      const float2 ml = attn_group_merge(S, base, gtid, 2 + gi);
+      float ov;
+      const float2 ml = attn_group_merge(S, base, gtid, 2 + gi, r0 == 0, ov);
       if (gtid < 64) {
-        const bf16 ov = __float2bfloat16(base[32 + gtid] / ml.y);
-        for (int r = 0; r < c_sp.R; ++r) c_sp.attn[((size_t)r * B + b) * d + h * 64 + gtid] = ov;
+        const bf16 o16 = __float2bfloat16(ov / ml.y);
+        for (int r = 0; r < c_sp.R; ++r) c_sp.attn[((size_t)r * B + b) * d + h * 64 + gtid] = o16;
       }
       S_SUB(2);
     }
@@ -1033,9 +1035,10 @@ __device__ __noinline__ uint32_t s_ph_cross(const SPhase* D, int pos, uint32_t s
     if (!(it.flags & 2)) continue;
     S_SUB(1);
     // ---- end of this group's segment of the task: publish the partial, the last arriver merges ----
-    const float2 ml = attn_group_merge(S, base, gtid, 2 + gi);
+    float ov;
+    const float2 ml = attn_group_merge(S, base, gtid, 2 + gi, (it.flags & 4) != 0, ov);
     float* part = c_sp.xpart + ((size_t)task * c_sp.part_stride + it.seg) * 66;
-    if (gtid < 64) part[2 + gtid] = base[32 + gtid];
+    if (gtid < 64) part[2 + gtid] = ov;
     if (gtid == 0) { part[0] = ml.x; part[1] = ml.y; }
     named_bar(2 + gi, 128);   // the group's partial (and raw scores) are written; one acq_rel atomic publishes them
     const int ns = it.ns;
