@@ -147,6 +147,11 @@ class AutomaticSpeechRecognitionPipeline:
                             # only; None/False -> <|notimestamps|> prompt and no timestamp rules
                             return_timestamps=bool(return_timestamps), return_token_timestamps=(return_timestamps == "word"),
                             language=gk.get("language"), task=gk.get("task"))
+        if batch_size > G.MAX_DECODE_BATCH and opts.hf_batch_compat and opts.return_token_timestamps:
+            import warnings
+            warnings.warn(f"batch_size={batch_size} > {G.MAX_DECODE_BATCH}: chunks are decoded in groups of {G.MAX_DECODE_BATCH} and "
+                          "hf_batch_compat's batch-wide alignment length applies per group (HF applies it per pipeline batch)",
+                          stacklevel=3)
         stats = {"chunks": len(plan), "decode_steps": 0, "generate_passes": 0, "h2d_bytes": 0, "d2h_bytes": 0}
         outputs: List[List[Dict]] = [[] for _ in waves]
         for b0 in range(0, len(plan), batch_size):

@@ -30,6 +30,10 @@ TIME_PRECISION = 0.02
 TIME_PRECISION_FEATURES = 0.01
 INPUT_STRIDE = 2
 NUM_SEGMENT_FRAMES = 3000
+# Rows per cw_decode_greedy call (the step kernel's shared-memory plan covers B <= 16). The reference CLI's batch_size is
+# 16 (REF/transcribe.py:27), so its batches map 1:1 onto decode calls. A pipeline batch_size above 16 is decoded in groups
+# of 16 and the hf_batch_compat T_batch semantics then apply per group of 16, not per pipeline batch — a documented
+# difference from HF at batch_size > 16 (asr_pipeline warns once).
 MAX_DECODE_BATCH = 16
 
 

@@ -7,7 +7,7 @@ import os
 import sys
 
 
-def transcribe_audio(file_path, model_id="nyrahealth/CrisperWhisper"):
+def transcribe_audio(file_path, model_id="nyrahealth/CrisperWhisper", adjust_pauses=False):
     import torch
     from transformers import AutoModelForSpeechSeq2Seq, AutoProcessor
     from .asr_pipeline import pipeline
@@ -15,13 +15,18 @@ def transcribe_audio(file_path, model_id="nyrahealth/CrisperWhisper"):
 
     if not torch.cuda.is_available():
         raise RuntimeError("crisperwhisper_b200 needs a B200 (sm_100a) GPU; there is no CPU path")
-    model = AutoModelForSpeechSeq2Seq.from_pretrained(model_id, torch_dtype=torch.bfloat16, low_cpu_mem_usage=False,
+    # float32 on the host: pack_state_dict does the single bf16 rounding of the matrices, and LayerNorm gamma/beta, biases
+    # and the positional tables reach their f32 slots unrounded.
+    model = AutoModelForSpeechSeq2Seq.from_pretrained(model_id, torch_dtype=torch.float32, low_cpu_mem_usage=False,
                                                       use_safetensors=True)
     processor = AutoProcessor.from_pretrained(model_id)
     pipe = pipeline("automatic-speech-recognition", model=model, tokenizer=processor.tokenizer,
                     feature_extractor=processor.feature_extractor, chunk_length_s=30, batch_size=16,
                     return_timestamps="word", device="cuda:0")
-    return adjust_pauses_for_hf_pipeline_output(pipe(file_path))
+    out = pipe(file_path)
+    # The reference CLI prints the raw pipeline output (REF/transcribe.py:33-35); the pause redistribution is the
+    # README's optional post-step (REF/README.md:174, REF/utils.py:1) — opt in with --adjust_pauses.
+    return adjust_pauses_for_hf_pipeline_output(out) if adjust_pauses else out
 
 
 def main():
@@ -29,12 +34,14 @@ def main():
     parser.add_argument("--f", type=str, required=True, help="Path to the audio file")
     parser.add_argument("--model_id", type=str, default="nyrahealth/CrisperWhisper")
     parser.add_argument("--vtt", type=str, default=None, help="also write the word timestamps as WebVTT (REF/app.py:74-82)")
+    parser.add_argument("--adjust_pauses", action="store_true",
+                        help="redistribute pauses between words (REF/utils.py:1 adjust_pauses_for_hf_pipeline_output, REF/README.md:174)")
     args = parser.parse_args()
     if not os.path.exists(args.f):
         print(f"Error: The file '{args.f}' does not exist.")
         sys.exit(1)
     try:
-        transcription = transcribe_audio(args.f, args.model_id)
+        transcription = transcribe_audio(args.f, args.model_id, args.adjust_pauses)
         print("Transcription:")
         print(transcription["text"])
         if args.vtt:
