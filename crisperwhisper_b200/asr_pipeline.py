@@ -129,7 +129,34 @@ class AutomaticSpeechRecognitionPipeline:
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------------------------------------------
+    _GENERATE_KEYS = {"max_new_tokens", "max_length", "hf_batch_compat", "force_unique_generate_call", "suppress_eos",
+                      "init_tokens", "language", "task", "return_timestamps", "return_token_timestamps", "num_beams", "do_sample",
+                      "temperature", "compression_ratio_threshold", "logprob_threshold", "no_speech_threshold", "prompt_ids",
+                      "condition_on_prev_tokens", "num_frames"}
+
+    @classmethod
+    def _check_generate_kwargs(cls, gk: Dict):
+        """The device path is the reference's default decode: greedy, one pass per window (REF/transcribe.py passes no
+        generate_kwargs; HF generation_whisper.py:641-700 then uses temperature 0 and no fallback thresholds).  Anything that
+        asks for another strategy fails here instead of being silently ignored."""
+        unknown = sorted(set(gk) - cls._GENERATE_KEYS)
+        if unknown:
+            raise ValueError(f"generate_kwargs not understood by crisperwhisper_b200: {unknown}")
+        t = gk.get("temperature")
+        temps = list(t) if isinstance(t, (list, tuple)) else [t]
+        if any(x not in (None, 0, 0.0) for x in temps) or gk.get("do_sample"):
+            raise NotImplementedError("sampling / temperature fallback is not implemented: cw_decode_greedy is the greedy "
+                                      "decode the reference runs by default (temperature 0)")
+        if gk.get("num_beams") not in (None, 1):
+            raise NotImplementedError("beam search is not implemented (the reference decodes with num_beams=1)")
+        for k in ("compression_ratio_threshold", "logprob_threshold", "no_speech_threshold"):
+            if gk.get(k) is not None:
+                raise NotImplementedError(f"{k}: the fallback / no-speech heuristics of HF generate_with_fallback are not implemented")
+        if gk.get("prompt_ids") is not None or gk.get("condition_on_prev_tokens"):
+            raise NotImplementedError("prompt_ids / condition_on_prev_tokens are not implemented")
+
     def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict, return_timestamps="word") -> List[List[Dict]]:
+        self._check_generate_kwargs(gk)
         eng = self.engine
         plan = []  # (input index, start, length, left, right, is_last, with_stride)
         for wi, wave in enumerate(waves):

@@ -94,3 +94,17 @@ def test_multilingual_model_without_any_language_source_raises():
                          no_timestamps_id=363, alignment_heads=[[0, 0]], decoder_start_token_id=257, is_multilingual=True)
     with pytest.raises(ValueError):
         G.init_token_template(cfg, G.GenOptions(), 1)
+
+
+def test_unsupported_generate_kwargs_fail_loudly():
+    """Decoding strategies the device path does not implement are refused, not ignored (HF would change the transcript)."""
+    import pytest
+    from crisperwhisper_b200.asr_pipeline import AutomaticSpeechRecognitionPipeline as P
+    P._check_generate_kwargs({"max_new_tokens": 8, "language": "en", "task": "transcribe", "temperature": 0.0, "num_beams": 1})
+    for bad in ({"temperature": (0.0, 0.2, 0.4)}, {"temperature": 0.7}, {"do_sample": True}, {"num_beams": 5},
+                {"logprob_threshold": -1.0}, {"compression_ratio_threshold": 1.35}, {"no_speech_threshold": 0.6},
+                {"prompt_ids": [1, 2]}, {"condition_on_prev_tokens": True}):
+        with pytest.raises(NotImplementedError):
+            P._check_generate_kwargs(bad)
+    with pytest.raises(ValueError):
+        P._check_generate_kwargs({"top_k": 5})
