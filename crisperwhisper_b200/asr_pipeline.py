@@ -121,6 +121,11 @@ class AutomaticSpeechRecognitionPipeline:
         rt = return_timestamps if return_timestamps is not None else self.return_timestamps
         return self._postprocess(model_outputs, rt)
 
+    def transcribe_bytes(self, audio_bytes: bytes) -> Dict:
+        """REF/app.py:99-103 `transcribe`: the demo's byte front-end (standardise, / 8, resample) + word timestamps."""
+        waveform = A.process_audio_bytes(audio_bytes, self._resample)
+        return self(waveform[0, :], return_timestamps="word")
+
     def _resample(self, x: np.ndarray, sr_in: int) -> np.ndarray:
         """Host waveform at sr_in -> 16 kHz through cw_resample (HF preprocess :394-408 calls torchaudio here)."""
         dev = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.engine.device)

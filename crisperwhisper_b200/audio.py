@@ -34,6 +34,23 @@ def read_wav(src) -> Tuple[np.ndarray, int]:
     return x, int(sr)
 
 
+def process_audio_bytes(audio_bytes, resampler=None) -> np.ndarray:
+    """The demo app's front-end (REF/app.py:85-96): WAV bytes -> raw sample values as float32 (no PCM scaling), standardised
+    to zero mean / unit std over the whole file, divided by 8, resampled to 16 kHz -> float32 waveform `[1, n]` (the caller
+    transcribes row 0, REF/app.py:99-103).  `resampler(x, sr_in) -> x16k` is Engine.resample (cw_resample = the kernel
+    torchaudio.transforms.Resample applies); the reference's side effect of writing sample.wav is not reproduced."""
+    from scipy.io import wavfile
+    sr, y = wavfile.read(io.BytesIO(bytes(audio_bytes)))
+    y = y.astype(np.float32)
+    y = (y - np.mean(y)) / np.std(y)
+    y = np.ascontiguousarray(y / 8, dtype=np.float32)
+    if int(sr) != SAMPLING_RATE:
+        if resampler is None:
+            raise ValueError(f"input is at {sr} Hz: pass a resampler (the pipeline uses Engine.resample) or 16 kHz audio")
+        y = np.ascontiguousarray(resampler(y, int(sr)), dtype=np.float32)
+    return y[None, :]
+
+
 def normalize_input(inputs, resampler=None) -> np.ndarray:
     """str (wav path) | bytes (wav file) | np.ndarray | {"array"|"raw", "sampling_rate"} -> float32 mono @16 kHz
     (automatic_speech_recognition.py:342-417).  Inputs at another rate go through `resampler(x, sr_in) -> x16k`, which the

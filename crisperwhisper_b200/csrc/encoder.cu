@@ -105,7 +105,7 @@ __device__ __forceinline__ bf16* swz(bf16* base, int row, int col) {
   return base + row * 64 + ((((col >> 3) ^ (row & 7)) << 3) | (col & 7));
 }
 
-__global__ void __launch_bounds__(kAThreads) attention_enc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+__global__ void __launch_bounds__(kAThreads, 2) attention_enc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                  int S, int d) {
   __shared__ __align__(128) bf16 sQ[kAQ * 64];
   __shared__ __align__(128) bf16 sK[2][kAK * 64];

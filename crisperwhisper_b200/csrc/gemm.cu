@@ -14,6 +14,8 @@
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <initializer_list>
+#include <unordered_map>
 #include "gemm.cuh"
 
 namespace cw {
@@ -349,8 +351,25 @@ __global__ void gemm_check_kernel(const bf16* __restrict__ A, const bf16* __rest
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
+// Encoded tensor maps are cached by (base, extents, strides, box): an encoder pass issues ~230 GEMMs over a handful of
+// distinct operands per layer, and cuTensorMapEncodeTiled costs microseconds of host time each.
+struct MapKey {
+  const void* base; uint64_t K, rows, batch, rs, bs; uint32_t box_rows; int rank;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && K == o.K && rows == o.rows && batch == o.batch && rs == o.rs && bs == o.bs && box_rows == o.box_rows &&
+           rank == o.rank;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.K, k.rows, k.batch, k.rs, k.bs, (uint64_t)k.box_rows, (uint64_t)k.rank}) h = (h ^ v) * 0x100000001B3ull;
+    return (size_t)h;
+  }
+};
 struct GemmState {
   PFN_cuTensorMapEncodeTiled_v12000 encode;
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
 };
 
 static int get_state(cw_ctx* ctx, GemmState** out) {
@@ -375,6 +394,9 @@ void gemm_state_free(cw_ctx* ctx) {
 // 3-D bf16 tensor map {K, rows, batch} with a [64 x box_rows x 1] SWIZZLE_128B box.
 static int make_map(GemmState* s, CUtensorMap* map, const void* base, uint64_t K, uint64_t rows, uint64_t batch,
                     uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, int rank) {
+  const MapKey key{base, K, rows, batch, row_stride_elems, batch_stride_elems, box_rows, rank};
+  auto hit = s->maps.find(key);
+  if (hit != s->maps.end()) { *map = hit->second; return CW_OK; }
   cuuint64_t dims[3] = {K, rows, batch};
   cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
   cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, 1};
@@ -385,6 +407,8 @@ static int make_map(GemmState* s, CUtensorMap* map, const void* base, uint64_t K
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CW_REQUIRE(r == CUDA_SUCCESS, CW_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  if (s->maps.size() >= 4096) s->maps.clear();   // workspaces move between calls: bound the cache
+  s->maps.emplace(key, *map);
   return CW_OK;
 }
 

@@ -185,3 +185,25 @@ def test_retrieve_segment_matches_hf_randomised():
             assert tuple(a["idxs"]) == tuple(b["idxs"])
             assert float(a["start"]) == float(b["start"]) and float(a["end"]) == float(b["end"]), (case, seq)
             assert np.array_equal(a["token_timestamps"], b["token_timestamps"].numpy()), (case, seq)
+
+
+def test_process_audio_bytes_matches_reference_app():
+    """REF/app.py:85-96 restated: raw sample values, (y - mean) / std, / 8, resample to 16 kHz, shape [1, n]."""
+    import io
+    from scipy.io import wavfile
+    from crisperwhisper_b200 import audio as A
+    rs = np.random.RandomState(4)
+    pcm = (rs.randn(4000) * 3000).astype(np.int16)
+    buf = io.BytesIO()
+    wavfile.write(buf, 16000, pcm)
+    got = A.process_audio_bytes(buf.getvalue())
+    y = pcm.astype(np.float32)
+    want = ((y - np.mean(y)) / np.std(y)) / 8
+    assert got.shape == (1, 4000) and got.dtype == np.float32 and np.array_equal(got[0], want.astype(np.float32))
+    buf = io.BytesIO()
+    wavfile.write(buf, 8000, pcm)
+    calls = []
+    got = A.process_audio_bytes(buf.getvalue(), lambda x, sr: (calls.append((len(x), sr)), np.repeat(x, 2))[1])
+    assert calls == [(4000, 8000)] and got.shape == (1, 8000)
+    with pytest.raises(ValueError):
+        A.process_audio_bytes(buf.getvalue())
