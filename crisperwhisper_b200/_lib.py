@@ -69,6 +69,11 @@ EXPORTS = {
     "cw_resample_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cw_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
                               C.c_size_t, C.c_void_p]),
+    "cw_words_from_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "cw_launch_count": (C.c_longlong, [C.c_void_p]),
     "cw_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "cw_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcrisper.so")
-SOURCES = ["api.cu", "logmel.cu", "align.cu", "gemm.cu", "encoder.cu", "decoder.cu", "resample.cu"]
+SOURCES = ["api.cu", "logmel.cu", "align.cu", "gemm.cu", "encoder.cu", "decoder.cu", "resample.cu", "postproc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false"]

@@ -18,9 +18,17 @@ functions on randomised token streams, strides, prompts and language switches):
   * word grouping and punctuation merging as in the reference, one pass each.
 
 The tokenizer stays the caller's: ids of special tokens, language names and the eos boundary are read from it.
+
+The hot configuration (`return_timestamps="word"`, byte-level vocabulary) runs natively: `cw_words_from_tokens`
+(csrc/postproc.cu, declared in include/crisper.h) is the same algorithm in C++ behind the C-ABI, fed with the byte table and
+special-token tables built here once per tokenizer.  It answers CW_POST_PUNT for anything it does not model (and for inputs on
+which the reference raises); this module then runs the Python path below, which is also what `CW_POSTPROC=python` forces.
+tests/test_postproc_native_cpu.py holds the two to identical results on the randomised streams of tests/test_decode_asr.py.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -142,6 +150,9 @@ class WordDecoder:
         self._lang: Dict[int, Optional[str]] = {}
         self._bytes: Dict[int, Optional[bytes]] = {}
         self._bytes_ok = self._probe_byte_level()
+        self._native = None          # vocabulary tables for cw_words_from_tokens, built on first use
+        self.native_calls = 0        # outputs answered by the native path / handed back to the Python path
+        self.native_punts = 0
 
     # -- token text -----------------------------------------------------------------------------------------------
     def _token_bytes(self, tid: int) -> Optional[bytes]:
@@ -256,12 +267,126 @@ class WordDecoder:
         extra = {"language": language} if return_language else {}
         return [{"text": w, "timestamp": (stamps[ix[0]][0], stamps[ix[-1]][1]), **extra} for w, ix in zip(words, idx)]
 
+    # -- native path (csrc/postproc.cu) -----------------------------------------------------------------------------
+    def _native_tables(self):
+        """Byte spelling of every text token + special / language tables, as flat arrays for cw_words_from_tokens."""
+        if self._native is not None:
+            return self._native
+        from transformers.models.whisper.tokenization_whisper import LANGUAGES
+        from . import _lib as L
+        lib = L.load()
+        eos = int(self.eos_id)
+        n_ids = max(len(self.tok), max(self.special_ids) + 1 if self.special_ids else 0)
+        pieces = self.tok.convert_ids_to_tokens(list(range(eos)))
+        special = np.zeros(n_ids, dtype=np.uint8)
+        special[[t for t in self.special_ids if 0 <= t < n_ids]] = 1
+        off = np.zeros(eos + 1, dtype=np.int64)
+        has = np.zeros(max(eos, 1), dtype=np.uint8)
+        blob = bytearray()
+        for t, piece in enumerate(pieces):
+            if not special[t] and isinstance(piece, str):
+                try:
+                    blob += bytes(_CHAR_TO_BYTE[c] for c in piece)
+                    has[t] = 1
+                except KeyError:
+                    pass
+            off[t + 1] = len(blob)
+        names = sorted(set(LANGUAGES.values()))
+        index = {nm: k for k, nm in enumerate(names)}
+        lang_of = np.full(n_ids, -1, dtype=np.int32)
+        for t in self.special_ids:
+            nm = self.language_of(t)
+            if nm is not None and 0 <= t < n_ids:
+                lang_of[t] = index[nm]
+        unspaced = np.asarray([nm in _UNSPACED_LANGUAGES for nm in names], dtype=np.uint8)
+        default = getattr(self.tok, "language", None) or "english"
+        self._native = dict(lib=lib, bytes=np.frombuffer(bytes(blob) or b"\0", dtype=np.uint8).copy(), off=off, has=has, eos=eos,
+                            special=special, lang_of=lang_of, n_ids=n_ids, unspaced=unspaced, names=names,
+                            default_unspaced=int(default in _UNSPACED_LANGUAGES),
+                            max_len=int(np.diff(off).max()) if eos else 1)
+        return self._native
+
+    def _decode_words_native(self, model_outputs, return_language, time_precision, segment_size):
+        """(text, {"chunks": words}) from cw_words_from_tokens, or None when the native path hands the input back."""
+        nt = self._native_tables()
+        runs, times, strides, has_stride = [], [], [], []
+        for output in model_outputs:
+            ids = np.asarray(output["tokens"])
+            tt = np.asarray(output["token_timestamps"])
+            if ids.ndim != 2 or tt.ndim != 2 or ids.shape[1] != tt.shape[1]:
+                return None
+            runs.append(np.ascontiguousarray(ids[0], dtype=np.int64))
+            times.append(np.ascontiguousarray(tt[0], dtype=np.float64))
+            st = output.get("stride")
+            has_stride.append(st is not None)
+            strides.append([float(x) for x in st] if st is not None else [0.0, 0.0, 0.0])
+        n_out = len(runs)
+        lens = np.asarray([len(r) for r in runs], dtype=np.int64)
+        out_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        flat = np.concatenate(runs) if n_out else np.zeros(0, np.int64)
+        if flat.size and (flat.min() < 0 or flat.max() >= nt["n_ids"]):
+            return None
+        tokens = np.ascontiguousarray(flat, dtype=np.int32)
+        ttimes = np.ascontiguousarray(np.concatenate(times) if n_out else np.zeros(0), dtype=np.float64)
+        strides_a = np.ascontiguousarray(np.asarray(strides, dtype=np.float64).reshape(-1, 3) if n_out else np.zeros((0, 3)))
+        has_a = np.asarray(has_stride, dtype=np.uint8)
+        n_tok = int(tokens.size)
+        text_cap = n_tok * nt["max_len"] + 16
+        word_cap = 3 * text_cap + 16
+        text_buf = np.empty(text_cap, dtype=np.uint8)
+        word_buf = np.empty(word_cap, dtype=np.uint8)
+        chunk_off = np.empty(n_tok + n_out + 3, dtype=np.int64)
+        word_off = np.empty(n_tok + 3, dtype=np.int64)
+        w_start = np.empty(n_tok + 2, dtype=np.float64)
+        w_end = np.empty(n_tok + 2, dtype=np.float64)
+        w_lang = np.empty(n_tok + 2, dtype=np.int32)
+        n_chunks, n_words, flags = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+
+        def p(a):
+            return a.ctypes.data_as(ctypes.c_void_p)
+        rc = nt["lib"].cw_words_from_tokens(
+            p(nt["bytes"]), p(nt["off"]), p(nt["has"]), nt["eos"], p(nt["special"]), p(nt["lang_of"]), nt["n_ids"], p(nt["unspaced"]),
+            len(nt["names"]), nt["default_unspaced"], int(self.timestamp_begin), int(self.prompt_id), int(self.sot_id), n_out,
+            p(tokens), p(ttimes), p(out_off), p(strides_a), p(has_a), float(time_precision), int(segment_size),
+            p(text_buf), text_cap, p(chunk_off), int(chunk_off.size - 1), ctypes.byref(n_chunks),
+            p(word_buf), word_cap, p(word_off), p(w_start), p(w_end), p(w_lang), int(w_lang.size), ctypes.byref(n_words),
+            ctypes.byref(flags))
+        if rc != 0:
+            return None
+        if flags.value & 1:
+            import logging
+            logging.getLogger(__name__).warning(
+                "no closing timestamp token: the audio may be cut mid-word, or the timestamp rules were off")
+        tb = text_buf.tobytes()
+        co = chunk_off[: n_chunks.value + 1].tolist()
+        text = "".join(tb[co[k]:co[k + 1]].decode("utf-8", errors="replace") for k in range(n_chunks.value))
+        wb = word_buf.tobytes()
+        wo = word_off[: n_words.value + 1].tolist()
+        ws, we, wl = w_start[: n_words.value].tolist(), w_end[: n_words.value].tolist(), w_lang[: n_words.value].tolist()
+        names = nt["names"]
+        words = []
+        for k in range(n_words.value):
+            item = {"text": wb[wo[k]:wo[k + 1]].decode("utf-8"), "timestamp": (ws[k], we[k])}
+            if return_language:
+                item["language"] = names[wl[k]] if wl[k] >= 0 else None
+            words.append(item)
+        return text, {"chunks": words}
+
     # -- the pass over the model outputs --------------------------------------------------------------------------
     def decode_asr(self, model_outputs, *, return_timestamps, return_language, time_precision, segment_size=1500):
         """Same contract as tokenizer._decode_asr (tokenization_whisper.py:901-1150): returns (text, optional) where
         optional is {} or {"chunks": [...]}.  `model_outputs` items hold "tokens" [1, L], optionally
         "token_timestamps" [1, L] (seconds, cumulative) and "stride" (chunk_len, left, right) in seconds."""
         word_mode = return_timestamps == "word"
+        if word_mode and self._bytes_ok and os.environ.get("CW_POSTPROC", "native") != "python":
+            try:
+                got = self._decode_words_native(model_outputs, return_language, time_precision, segment_size)
+            except (KeyError, TypeError, ValueError, IndexError):
+                got = None           # malformed outputs: the Python path raises what the reference raises
+            if got is not None:
+                self.native_calls += 1
+                return got
+            self.native_punts += 1
         ts0 = self.timestamp_begin
         language: Optional[str] = None
 

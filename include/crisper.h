@@ -34,7 +34,8 @@ typedef enum cw_status {
   CW_ERR_CUDA = -2,       /* CUDA runtime / driver error (message has the CUDA string) */
   CW_ERR_WORKSPACE = -3,  /* workspace too small */
   CW_ERR_STATE = -4,      /* call order (weights not loaded, ...) */
-  CW_ERR_UNSUPPORTED = -5 /* shape outside what the kernels are built for */
+  CW_ERR_UNSUPPORTED = -5, /* shape outside what the kernels are built for */
+  CW_POST_PUNT = 1         /* cw_words_from_tokens only: input outside what the native path models — use the Python path */
 } cw_status;
 
 typedef struct cw_ctx cw_ctx;
@@ -258,6 +259,30 @@ int cw_decode_pack(cw_ctx* ctx, void* buf, size_t bytes, void* stream);
  * cta_off_out i32 [n_cta + 1] item range of CTA c = [cta_off[c], cta_off[c+1]);  splits_out i32 [tasks] segments per task. */
 int cw_decode_cross_plan(int tasks, int n_frames, int chunk_rows, int n_cta, int32_t* items_out, int32_t* cta_off_out,
                          int32_t* splits_out);
+/* ---- host post-processing (no GPU): token ids + token timestamps -> word chunks, the step after cw_align.
+ * Replaces the caller's tokenizer._decode_asr (HF/models/whisper/tokenization_whisper.py:901-1150 with its helpers
+ * :1153-1405) for return_timestamps="word" on a byte-level BPE vocabulary; python mirror: crisperwhisper_b200/decode_asr.py.
+ * Vocabulary (built once per tokenizer by the caller):
+ *  tok_bytes / tok_off [eos_id + 1] / tok_has_bytes [eos_id]  byte spelling of every text token id < eos_id
+ *  is_special u8 [n_ids], lang_of i32 [n_ids] (language number of a <|xx|> token, else -1), lang_unspaced u8 [n_lang]
+ *  (languages written without spaces: words = unicode units), default_unspaced (tokenizer.language when no token said one),
+ *  timestamp_begin (<|0.00|>), prompt_id (<|startofprev|>), sot_id.
+ * Model outputs: n_outputs runs; tokens i32 and token_times f64 concatenated, run r = [out_off[r], out_off[r+1]);
+ *  strides f64 [n_outputs][3] = (chunk_len, left, right) seconds where has_stride[r] != 0.
+ * Results: text_buf = raw bytes of every closed chunk's merged token run, chunk c = [chunk_off[c], chunk_off[c+1])
+ *  (the caller decodes each chunk as UTF-8 with replacement and joins them: the "text" of the pipeline output);
+ *  word_buf = UTF-8 of every word, word w = [word_off[w], word_off[w+1]), word_start/word_end seconds, word_lang the
+ *  language number in force (-1: none); flags bit 0: the last chunk had no closing timestamp token.
+ * Returns CW_OK, CW_POST_PUNT (a token without byte spelling, or an input on which the reference raises: the caller runs
+ * the Python path, which answers or raises exactly like the reference), CW_ERR_WORKSPACE (output capacity), CW_ERR_INVALID. */
+int cw_words_from_tokens(const uint8_t* tok_bytes, const int64_t* tok_off, const uint8_t* tok_has_bytes, int32_t eos_id,
+                         const uint8_t* is_special, const int32_t* lang_of, int32_t n_ids, const uint8_t* lang_unspaced,
+                         int32_t n_lang, int32_t default_unspaced, int32_t timestamp_begin, int32_t prompt_id, int32_t sot_id,
+                         int32_t n_outputs, const int32_t* tokens, const double* token_times, const int64_t* out_off,
+                         const double* strides, const uint8_t* has_stride, double time_precision, int32_t segment_size,
+                         char* text_buf, int64_t text_cap, int64_t* chunk_off, int32_t chunk_cap, int32_t* n_chunks,
+                         char* word_buf, int64_t word_cap, int64_t* word_off, double* word_start, double* word_end,
+                         int32_t* word_lang, int32_t words_cap, int32_t* n_words, int32_t* flags);
 /* Number of kernel launches issued by this ctx since creation (bench.py `gpu_launches`). */
 long long cw_launch_count(const cw_ctx* ctx);
 /* Device time of the most recent call's dominant kernel is measured by the caller with events; these let

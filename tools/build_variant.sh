@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 O=crisperwhisper_b200/_obj
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c crisperwhisper_b200/csrc/decoder.cu -o /tmp/decoder_$name.o
 mkdir -p _ab
-nvcc -shared -o _ab/$name.so $O/api.o $O/logmel.o $O/align.o $O/gemm.o $O/encoder.o $O/resample.o /tmp/decoder_$name.o -gencode arch=compute_100a,code=sm_100a -cudart static
+nvcc -shared -o _ab/$name.so $O/api.o $O/logmel.o $O/align.o $O/gemm.o $O/encoder.o $O/resample.o $O/postproc.o /tmp/decoder_$name.o -gencode arch=compute_100a,code=sm_100a -cudart static
 python - <<PY
 import ctypes; ctypes.CDLL("_ab/$name.so"); print("built _ab/$name.so (loads)")
 PY
