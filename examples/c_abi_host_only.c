@@ -27,6 +27,32 @@ int main(void) {
   for (i = 0; i < 148; ++i)
     if (off[i + 1] - off[i] > worst) worst = off[i + 1] - off[i];
   printf("cross_plan worst_cta_chunks %d\n", worst);
+  /* host post-processing: a 6-id toy vocabulary (0 " hi", 1 ",", 2 " there"; 3 = eos, 4 = <|startofprev|>, 5 = sot,
+   * 6.. = timestamps), one output "<|0.00|> hi, there<|1.00|>" with cumulative token times */
+  {
+    static const uint8_t tb[] = " hi, there";
+    static const int64_t toff[4] = {0, 3, 4, 10};
+    static const uint8_t has[3] = {1, 1, 1};
+    static const uint8_t special[60] = {0, 0, 0, 1, 1, 1};
+    int32_t lang_of[60];
+    static const uint8_t unspaced[1] = {0};
+    static const int32_t toks[5] = {6, 0, 1, 2, 6 + 50};
+    static const double times[5] = {0.0, 0.30, 0.36, 0.80, 1.0};
+    static const int64_t ooff[2] = {0, 5};
+    static const double strides[3] = {0, 0, 0};
+    static const uint8_t has_stride[1] = {0};
+    char text[64], wtext[64];
+    int64_t coff[8], woff[8];
+    double ws[8], we[8];
+    int32_t wl[8], nc = 0, nw = 0, fl = 0, k;
+    for (k = 0; k < 60; ++k) lang_of[k] = -1;
+    if (cw_words_from_tokens(tb, toff, has, 3, special, lang_of, 60, unspaced, 1, 0, 6, 4, 5, 1, toks, times, ooff, strides,
+                             has_stride, 0.02, 1500, text, 64, coff, 7, &nc, wtext, 64, woff, ws, we, wl, 8, &nw, &fl) != CW_OK)
+      return 4;
+    printf("words %d:", nw);
+    for (k = 0; k < nw; ++k) printf(" [%.*s %.2f-%.2f]", (int)(woff[k + 1] - woff[k]), wtext + woff[k], ws[k], we[k]);
+    printf("\n");
+  }
   /* a device entry point without a context must fail cleanly, never crash */
   if (cw_resample(NULL, NULL, 0, 44100, 16000, NULL, 0, NULL, 0, NULL) == CW_OK) return 3;
   printf("null ctx error: %s\n", cw_last_error());

@@ -115,3 +115,4 @@ def test_header_is_valid_c99_and_links_from_plain_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "resample_out_len 480000" in r.stdout and "worst_cta_chunks 21" in r.stdout and "ctx is NULL" in r.stdout
+    assert "words 2: [ hi, 0.00-0.36] [ there 0.36-0.80]" in r.stdout, r.stdout
