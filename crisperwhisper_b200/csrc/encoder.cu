@@ -152,14 +152,14 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_enc_kernel(const bf16*
 
   for (int t = 0; t < n_tiles; ++t) {
     const int buf = t & 1;
+    // tile t (requested a whole tile ago) has landed for this thread; the barrier publishes it and also tells everyone that
+    // tile t-1 is no longer being read, so its buffer can take tile t+1 right away — one barrier per tile
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
     if (t + 1 < n_tiles) {
       load_kv(t + 1, buf ^ 1);
       asm volatile("cp.async.commit_group;\n" ::);
-      asm volatile("cp.async.wait_group 1;\n" ::);
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::);
     }
-    __syncthreads();
     if (t == 0) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_enc_kernel(const bf16*
         mma_bf16_16816(o[2 * jp + 1], pf[kk], b2, b3);
       }
     }
-    __syncthreads();  // all warps done with buf before it is refilled two iterations later
   }
   // finalize
 #pragma unroll
