@@ -765,7 +765,8 @@ __device__ __noinline__ uint32_t s_ph_fc2g(const SPhase* D, int pos, uint32_t se
   S_SUB(4);
   const unsigned int target = 3u * (unsigned int)(pos * c_sp.dec_layers + D->l + 1);
   if (kc != 0) {
-    __threadfence();
+    // the CTA barrier orders every thread's partial-sum stores before thread 0's release (cumulative at gpu scope), exactly
+    // as in the grid barrier: no per-thread fence
     cons_bar();
     if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c_sp.kflag + gq) : "memory");
   } else {
