@@ -89,7 +89,7 @@ class AutomaticSpeechRecognitionPipeline:
 
     # ------------------------------------------------------------------------------------------------------
     def __call__(self, inputs, return_timestamps=None, generate_kwargs: Optional[Dict] = None, batch_size=None,
-                 chunk_length_s=None, **kw):
+                 chunk_length_s=None, return_language=None, **kw):
         """Single input -> dict; list of inputs -> list of dicts.  Like HF's DataLoader-backed pipeline, chunks of
         different inputs share batches of `batch_size` (HF/pipelines/base.py:1298-1318)."""
         is_list = isinstance(inputs, (list, tuple))
@@ -97,11 +97,18 @@ class AutomaticSpeechRecognitionPipeline:
         rt = return_timestamps if return_timestamps is not None else self.return_timestamps
         gk = dict(self.generate_kwargs)
         gk.update(generate_kwargs or {})
+        # the reference pipeline's other call arguments (_sanitize_parameters, automatic_speech_recognition.py:262-300)
+        if kw.get("max_new_tokens") is not None:
+            gk["max_new_tokens"] = kw["max_new_tokens"]
+        stride = kw.get("stride_length_s", self.stride_length_s)
+        unknown = sorted(set(kw) - {"max_new_tokens", "stride_length_s", "ignore_warning", "decoder_kwargs", "num_workers"})
+        if unknown:
+            raise TypeError(f"pipeline call: unexpected keyword arguments {unknown}")
         bs = self.batch_size if batch_size is None else max(1, int(batch_size))
         cl = self.chunk_length_s if chunk_length_s is None else chunk_length_s
         waves = [A.normalize_input(x, self._resample) for x in items]
-        per_input = self._run(waves, cl, bs, gk, rt)
-        results = [self._postprocess(mo, rt) for mo in per_input]
+        per_input = self._run(waves, cl, bs, gk, rt, stride_length_s=stride)
+        results = [self._postprocess(mo, rt, return_language) for mo in per_input]
         return results if is_list else results[0]
 
     def forward(self, inputs, return_timestamps=None, generate_kwargs: Optional[Dict] = None, batch_size=None, chunk_length_s=None):
@@ -117,9 +124,9 @@ class AutomaticSpeechRecognitionPipeline:
         waves = [A.normalize_input(x, self._resample) for x in items]
         return self._run(waves, cl, bs, gk, rt)
 
-    def postprocess(self, model_outputs: List[Dict], return_timestamps=None):
+    def postprocess(self, model_outputs: List[Dict], return_timestamps=None, return_language=None):
         rt = return_timestamps if return_timestamps is not None else self.return_timestamps
-        return self._postprocess(model_outputs, rt)
+        return self._postprocess(model_outputs, rt, return_language)
 
     def transcribe_bytes(self, audio_bytes: bytes) -> Dict:
         """REF/app.py:99-103 `transcribe`: the demo's byte front-end (standardise, / 8, resample) + word timestamps."""
@@ -160,13 +167,15 @@ class AutomaticSpeechRecognitionPipeline:
         if gk.get("prompt_ids") is not None or gk.get("condition_on_prev_tokens"):
             raise NotImplementedError("prompt_ids / condition_on_prev_tokens are not implemented")
 
-    def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict, return_timestamps="word") -> List[List[Dict]]:
+    def _run(self, waves: List[np.ndarray], chunk_length_s, batch_size: int, gk: Dict, return_timestamps="word",
+             stride_length_s="default") -> List[List[Dict]]:
         self._check_generate_kwargs(gk)
         eng = self.engine
         plan = []  # (input index, start, length, left, right, is_last, with_stride)
         for wi, wave in enumerate(waves):
             if chunk_length_s:
-                plan += [(wi,) + p + (True,) for p in A.chunk_plan(len(wave), chunk_length_s, self.stride_length_s)]
+                stride = self.stride_length_s if isinstance(stride_length_s, str) else stride_length_s
+                plan += [(wi,) + p + (True,) for p in A.chunk_plan(len(wave), chunk_length_s, stride)]
             else:
                 if len(wave) > A.N_SAMPLES:
                     raise NotImplementedError("inputs longer than 30 s need chunk_length_s (the reference always sets 30)")
@@ -211,8 +220,9 @@ class AutomaticSpeechRecognitionPipeline:
         return outputs
 
     # ------------------------------------------------------------------------------------------------------
-    def _postprocess(self, model_outputs: List[Dict], return_timestamps):
-        """postprocess (automatic_speech_recognition.py:562-656) for the seq2seq_whisper type."""
+    def _postprocess(self, model_outputs: List[Dict], return_timestamps, return_language=None):
+        """postprocess (automatic_speech_recognition.py:562-656) for the seq2seq_whisper type; `return_language` adds the
+        language of every chunk / word, as the reference pipeline's call argument of the same name (:296-299)."""
         if self.tokenizer is None:
             return {"tokens": [o["tokens"][0] for o in model_outputs],
                     "token_timestamps": [o["token_timestamps"][0] for o in model_outputs if "token_timestamps" in o]}
@@ -224,7 +234,7 @@ class AutomaticSpeechRecognitionPipeline:
         if self._words is None or self._words.tok is not self.tokenizer:
             self._words = D.WordDecoder(self.tokenizer)
         text, optional = self._words.decode_asr(model_outputs, return_timestamps=return_timestamps,
-                                                return_language=None, time_precision=time_precision)
+                                                return_language=return_language, time_precision=time_precision)
         return {"text": text, **optional}
 
 

@@ -108,3 +108,33 @@ def test_unsupported_generate_kwargs_fail_loudly():
             P._check_generate_kwargs(bad)
     with pytest.raises(ValueError):
         P._check_generate_kwargs({"top_k": 5})
+
+
+def test_call_arguments_of_the_reference_pipeline(monkeypatch):
+    """return_language / max_new_tokens / stride_length_s are call arguments of the reference pipeline
+    (automatic_speech_recognition.py:262-300); anything else is a TypeError there and here."""
+    from crisperwhisper_b200.asr_pipeline import AutomaticSpeechRecognitionPipeline as P
+    seen = {}
+
+    class Fake(P):
+        def __init__(self):
+            self.generate_kwargs, self.batch_size, self.chunk_length_s, self.return_timestamps = {}, 2, 30, "word"
+            self.stride_length_s = None
+
+        def _resample(self, x, sr):
+            return x
+
+        def _run(self, waves, cl, bs, gk, rt, stride_length_s="default"):
+            seen.update(gk=gk, stride=stride_length_s, rt=rt)
+            return [[] for _ in waves]
+
+        def _postprocess(self, mo, rt, return_language=None):
+            seen["lang"] = return_language
+            return {"text": ""}
+
+    pipe = Fake()
+    pipe(np.zeros(16000, np.float32), max_new_tokens=7, stride_length_s=(4, 2), return_language=True, ignore_warning=True)
+    assert seen["gk"]["max_new_tokens"] == 7 and seen["stride"] == (4, 2) and seen["lang"] is True and seen["rt"] == "word"
+    import pytest
+    with pytest.raises(TypeError):
+        pipe(np.zeros(16000, np.float32), top_k=3)
